@@ -1,0 +1,695 @@
+// grail_kernels.cuh -- the sm_100a kernels of the waveform-generation path.
+//
+//   k_jitter_schedule  exact wrap schedule of the value-noise phase clock      (src/lib.rs:242-251)
+//   k_frequency        bit-exact per-sample fundamental F_t                     (src/lib.rs:861-931, 753-763)
+//   k_phase_serial     bit-exact carrier phase + polyBLEP saw, one lane/utt     (src/lib.rs:503-525)
+//   k_formant<NW>      noise, low-pass, turbulence, SVF band-pass, formant sum  (src/lib.rs:528-577, 764-773)
+//
+// Exactness classes: the clocks, the LCG streams, F_t, the carrier phase and the saw are
+// computed with strict, never-contracted f32 ops in the reference's order and are bit-identical to it.
+// Everything 8-wide and downstream of the saw is in the tolerance class (FMA, rcp.approx, re-association).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "grail_common.cuh"
+
+namespace grail {
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident plan
+// ------------------------------------------------------------------------------------------------
+constexpr int SEQ_WORDS = 52;      // sizeof(grail_seq_elem) / 4
+constexpr int SE_HAS = 0;          // word index of has_elem
+constexpr int SE_FREQ = 1;         // elem.frequency
+constexpr int SE_ARR = 2;          // first array word: formant_freq[0]; array k at SE_ARR + 8k
+constexpr int SE_LEN = 50;
+constexpr int SE_BLEND = 51;
+enum { P_FF = 0, P_BW = 1, P_SM = 2, P_BR = 3, P_TB = 4, P_AMP = 5 };
+
+struct UttDev {
+    uint32_t elem_first, n_elems;  // phonemes of this utterance in `elems` / `segs`
+    uint32_t n_samples;
+    uint32_t jit_sched;            // index into JitSchedDev
+    uint32_t item_first, n_items;  // work items (time chunks) of this utterance, consecutive
+    uint32_t n_active;             // number of formants whose amplitude is not identically zero
+    uint8_t  active[8];            // their indices, ascending
+    uint64_t out_off;              // first output sample
+    uint64_t f_off;                // first entry in the linear F_t scratch (multiple of 8)
+    grail_voice_params voice;
+    float    init_phase;           // carrier phase at sample 0 (0 for a fresh utterance)
+};
+
+struct JitSchedDev {
+    float    inc;                  // voice.jitter_frequency
+    uint32_t n_max;                // samples the schedule must cover
+    uint32_t rec_first, rec_cap;   // slice of the JitRec array
+    uint32_t n_recs;               // written by k_jitter_schedule
+    uint32_t overflow;
+};
+
+struct ItemDev {
+    uint32_t utt;
+    uint32_t n0;                   // first sample (multiple of chunk_len)
+    uint32_t len;                  // samples in this chunk
+    uint32_t pad;
+};
+
+struct PlanDev {
+    const float*        elems;     // n_elems_total x 52 words
+    const SegRec*       segs;      // one per phoneme
+    const UttDev*       utts;
+    const ItemDev*      items;
+    JitSchedDev*        jscheds;
+    JitRec*             jrecs;
+    float*              F;         // linear, per utterance at f_off
+    float*              saw;       // tiled: [group][j/8][lane][8]
+    float*              phase_dbg; // optional linear carrier phase tap (same indexing as F), may be null
+    uint32_t*           err;       // device error word
+    uint32_t n_utts, n_items, n_groups, n_jscheds;
+    uint32_t chunk_len;            // CL, multiple of 32
+    float    warmup_nepers;
+};
+
+enum : uint32_t { DEV_ERR_JIT_OVERFLOW = 1u, DEV_ERR_SEG = 2u };
+
+__device__ __forceinline__ size_t saw_index(uint32_t item, uint32_t j, uint32_t chunk_len)
+{
+    return ((size_t)(item >> 5) * (chunk_len >> 3) + (j >> 3)) * 256u + (item & 31u) * 8u + (j & 7u);
+}
+
+__device__ __forceinline__ float frcp(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// largest index i in [0, n) with key(i) <= v; the caller guarantees key(0) <= v
+template <typename F>
+__device__ __forceinline__ uint32_t last_le(uint32_t n, F key, int64_t v)
+{
+    uint32_t lo = 0, hi = n; // invariant: key(lo) <= v, key(hi) > v (hi == n is +inf)
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((int64_t)key(mid) <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: jitter schedule.  One lane per distinct jitter_frequency; walks the value-noise phase clock
+// binade by binade (closed form) and records every wrap.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_jitter_schedule(PlanDev P)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.n_jscheds) return;
+    JitSchedDev& S = P.jscheds[s];
+    JitRec* rec = P.jrecs + S.rec_first;
+    const float inc = S.inc;
+    int64_t n = -1;
+    float ph = 0.0f;
+    uint32_t w = 0;
+    rec[0].n = -1;
+    rec[0].phase = 0.0f;
+    const int64_t last = (int64_t)S.n_max - 1;
+    while (n < last) {
+        const ClockRun r = clock_asc_run(ph, inc, (uint64_t)(last - n));
+        n += (int64_t)r.steps;
+        if (r.stuck || !(r.x > 1.0f)) break;
+        ph = ssub(r.x, 1.0f); // src/lib.rs:246
+        ++w;
+        if (w >= S.rec_cap) {
+            S.overflow = 1;
+            atomicOr(P.err, DEV_ERR_JIT_OVERFLOW);
+            --w;
+            break;
+        }
+        rec[w].n = (int32_t)n;
+        rec[w].phase = ph;
+    }
+    S.n_recs = w + 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Segment view used by K1 (frequency lane only)
+// ------------------------------------------------------------------------------------------------
+struct FreqSeg {
+    float xf, yf;   // blend endpoints: out = xf*(1-alpha) + yf*alpha
+    float blend_len;
+    int   silent;   // both cur and next have no element: SynthesisElem::silent(), frequency 0.25
+};
+
+__device__ __forceinline__ FreqSeg load_freq_seg(const float* ue, uint32_t p, uint32_t n_elems)
+{
+    const float* cur = ue + (size_t)p * SEQ_WORDS;
+    const bool b_on = __float_as_uint(cur[SE_HAS]) != 0u;
+    bool c_on = false;
+    const float* nxt = cur + SEQ_WORDS;
+    if (p + 1 < n_elems) c_on = __float_as_uint(nxt[SE_HAS]) != 0u;
+    FreqSeg s;
+    s.blend_len = cur[SE_BLEND];
+    s.silent = 0;
+    if (b_on && c_on) { s.xf = nxt[SE_FREQ]; s.yf = cur[SE_FREQ]; }      // c.blend(b, alpha)          :902
+    else if (b_on)    { s.xf = cur[SE_FREQ]; s.yf = cur[SE_FREQ]; }      // b.copy_silent().blend(b)   :911
+    else if (c_on)    { s.xf = nxt[SE_FREQ]; s.yf = nxt[SE_FREQ]; }      // c.blend(c.copy_silent())   :920
+    else              { s.xf = 0.25f; s.yf = 0.25f; s.silent = 1; }      // SynthesisElem::silent()    :926
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: bit-exact F_t.  One lane per run of FREQ_RUN consecutive samples: the two clocks are evaluated in
+// closed form at the run start, then replayed literally; the scalar frequency path uses strict ops in
+// the reference's order (blend :406, value-noise lerp :254, jitter add :763).
+// ------------------------------------------------------------------------------------------------
+constexpr int FREQ_RUN = 128;
+
+__global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_item)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t item = (uint32_t)(t / runs_per_item);
+    const uint32_t run = (uint32_t)(t % runs_per_item);
+    if (item >= P.n_items) return;
+    const ItemDev it = P.items[item];
+    const uint32_t off = run * FREQ_RUN;
+    if (off >= it.len) return;
+    const uint32_t count = min((uint32_t)FREQ_RUN, it.len - off);
+    const uint32_t ns = it.n0 + off;
+    const UttDev& U = P.utts[it.utt];
+    const float* ue = P.elems + (size_t)U.elem_first * SEQ_WORDS;
+    const SegRec* segs = P.segs + U.elem_first;
+    const uint32_t n_elems = U.n_elems;
+    const float dt = sdiv(1.0f, U.voice.sample_rate); // src/lib.rs:944
+    const float jinc = U.voice.jitter_frequency;
+    const float dfreq = U.voice.jitter_delta_frequency;
+
+    // Sequencer state at sample ns
+    uint32_t p = last_le(n_elems, [&](uint32_t i) { return segs[i].start; }, (int64_t)ns);
+    float time = clock_desc_run(segs[p].time0, dt, ns - segs[p].start).x;
+    FreqSeg seg = load_freq_seg(ue, p, n_elems);
+
+    // value-noise state at sample ns
+    const JitSchedDev& JS = P.jscheds[U.jit_sched];
+    const JitRec* recs = P.jrecs + JS.rec_first;
+    const uint32_t w = last_le(JS.n_recs, [&](uint32_t i) { return recs[i].n; }, (int64_t)ns);
+    float jph = clock_asc_run(recs[w].phase, jinc, (uint64_t)((int64_t)ns - recs[w].n)).x;
+    uint32_t s_next = lcg_jump(U.voice.jitter_seed, jit_freq_cur_idx(w));
+    float cur = lcg_float(s_next);
+    s_next = lcg_step(s_next);
+    float nxt = lcg_float(s_next);
+
+    float* dst = P.F + U.f_off + ns;
+    // one sample of the scalar frequency path, strict ops in the reference's order
+    auto freq_sample = [&]() -> float {
+        float fb;
+        if (seg.silent) {
+            fb = 0.25f;
+        } else {
+            const float alpha = fminf(sdiv(time, seg.blend_len), 1.0f);                    // :899
+            fb = sadd(smul(seg.xf, ssub(1.0f, alpha)), smul(seg.yf, alpha));               // :406
+        }
+        const float n0 = sadd(smul(cur, ssub(1.0f, jph)), smul(nxt, jph));                 // :254
+        return sadd(fb, smul(n0, dfreq));                                                  // :763
+    };
+    for (uint32_t k0 = 0; k0 < count; k0 += 8) {
+        const bool quiet = (k0 + 8 <= count) && (time > 9.0f * dt) && (jph + 9.0f * jinc < 1.0f);
+        if (quiet) { // no hand-over and no wrap inside these 8 samples: literal clocks, no event tests
+            float buf[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                buf[k] = freq_sample();
+                time = ssub(time, dt);                                                     // :861
+                jph = sadd(jph, jinc);                                                     // :242
+            }
+            float4* d4 = reinterpret_cast<float4*>(dst + k0);
+            d4[0] = make_float4(buf[0], buf[1], buf[2], buf[3]);
+            d4[1] = make_float4(buf[4], buf[5], buf[6], buf[7]);
+        } else {
+            const uint32_t kend = min(k0 + 8, count);
+#pragma unroll 1
+            for (uint32_t k = k0; k < kend; ++k) {
+                dst[k] = freq_sample();
+                time = ssub(time, dt);                                                     // :861
+                if (time < 0.0f) {                                                         // :864
+                    ++p;
+                    if (p < n_elems) {
+                        time = sadd(time, ue[(size_t)p * SEQ_WORDS + SE_LEN]);             // :873
+                        seg = load_freq_seg(ue, p, n_elems);
+                    }
+                }
+                jph = sadd(jph, jinc);                                                     // :242
+                if (jph > 1.0f) {                                                          // :245
+                    jph = ssub(jph, 1.0f);
+                    cur = nxt;
+                    s_next = lcg_step(s_next);
+                    nxt = lcg_float(s_next);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 (serial form): bit-exact carrier phase and polyBLEP saw, one lane per utterance.  The f32 chain
+// phase <- RN(phase + F_t) is the only truly serial dependency of the path; blocks of 8 are run
+// speculatively as bare adds (4 cycles each) and redone carefully only when a wrap falls inside.
+// Output goes straight into the tiled layout k_formant reads with perfectly coalesced 128-bit loads.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float saw_sample(float phase, float f)
+{
+    float polyblep = 0.0f;
+    if (phase < f) {                                             // :503-506
+        const float t = sdiv(phase, f);
+        polyblep = ssub(ssub(smul(2.0f, t), smul(t, t)), 1.0f);
+    } else if (phase > ssub(1.0f, f)) {                          // :507-510
+        const float t = sdiv(ssub(phase, 1.0f), f);
+        polyblep = sadd(sadd(smul(t, t), smul(2.0f, t)), 1.0f);
+    }
+    return ssub(ssub(smul(2.0f, phase), 1.0f), polyblep);        // :517
+}
+
+__global__ void __launch_bounds__(32) k_phase_serial(PlanDev P)
+{
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= P.n_utts) return;
+    const UttDev& U = P.utts[u];
+    const uint32_t n = U.n_samples;
+    if (n == 0) return;
+    const float4* src = reinterpret_cast<const float4*>(P.F + U.f_off);
+    float* dbg = P.phase_dbg ? P.phase_dbg + U.f_off : nullptr;
+    const uint32_t CL = P.chunk_len;
+    float phase = U.init_phase;
+    uint32_t item = U.item_first, j = 0;
+    const uint32_t nblk = (n + 7) >> 3;
+    float4 fa = __ldg(src), fb = __ldg(src + 1);
+    for (uint32_t blk = 0; blk < nblk; ++blk) {
+        float f[8] = { fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w };
+        if (blk + 1 < nblk) { // prefetch the next block while the chain below runs
+            fa = __ldg(src + 2 * (blk + 1));
+            fb = __ldg(src + 2 * (blk + 1) + 1);
+        }
+        const uint32_t valid = min(8u, n - blk * 8);
+        float ph[9];
+        ph[0] = phase;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ph[k + 1] = sadd(ph[k], f[k]);
+        float fmin8 = f[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) fmin8 = fminf(fmin8, f[k]);
+        float s[8];
+        // speculation is valid when no wrap can have happened: increments positive => the chain is
+        // monotone, so its last value bounds all of them (NaNs fail the test and take the slow path)
+        if (valid == 8 && fmin8 > 0.0f && ph[8] < 1.0f) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s[k] = saw_sample(ph[k], f[k]);
+            if (dbg) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) dbg[blk * 8 + k] = ph[k];
+            }
+            phase = ph[8];
+        } else {
+#pragma unroll 1
+            for (uint32_t k = 0; k < 8; ++k) {
+                s[k] = 0.0f;
+                if (k < valid) {
+                    s[k] = saw_sample(phase, f[k]);
+                    if (dbg) dbg[blk * 8 + k] = phase;
+                    phase = sadd(phase, f[k]);                    // :520
+                    if (phase >= 1.0f) phase = ssub(phase, 1.0f); // :523-525
+                }
+            }
+        }
+        float4* dst = reinterpret_cast<float4*>(P.saw + saw_index(item, j, CL));
+        dst[0] = make_float4(s[0], s[1], s[2], s[3]);
+        dst[1] = make_float4(s[4], s[5], s[6], s[7]);
+        j += 8;
+        if (j >= CL) { j = 0; ++item; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: the dominant kernel.  CTA = one group of 32 work items (time chunks) x NW warps; warp w owns the
+// w-th active formant of each item's utterance, lane l owns chunk l.  Each lane replays the exact
+// clocks literally, generates its formant's parameters, noise, low-pass and SVF in registers, and
+// leaves v1 in a shared tile; every 32 samples the CTA sums the tile over formants (reference order)
+// and writes 128-byte rows.  Filter state at a chunk start comes from a warm-up over the preceding
+// samples, long enough that the zero-state error has decayed by exp(-warmup_nepers).
+// ------------------------------------------------------------------------------------------------
+struct FormantSeg {
+    float x[6], d[6];  // parameter = x + alpha * d   (d = y - x)
+    float inv_bl;
+};
+
+__device__ __forceinline__ void seg_endpoints(const float* ue, uint32_t p, uint32_t n_elems, int fi, float* x, float* y,
+                                              float* blend_len)
+{
+    const float* cur = ue + (size_t)p * SEQ_WORDS;
+    const float* nxt = cur + SEQ_WORDS;
+    const bool b_on = __float_as_uint(cur[SE_HAS]) != 0u;
+    const bool c_on = (p + 1 < n_elems) && (__float_as_uint(nxt[SE_HAS]) != 0u);
+    *blend_len = cur[SE_BLEND];
+    if (!b_on && !c_on) { // SynthesisElem::silent() :367-377
+        x[P_FF] = y[P_FF] = 0.25f; x[P_BW] = y[P_BW] = 0.25f; x[P_SM] = y[P_SM] = 0.25f;
+        x[P_BR] = y[P_BR] = 0.0f;  x[P_TB] = y[P_TB] = 0.0f;  x[P_AMP] = y[P_AMP] = 0.0f;
+        return;
+    }
+    const float* xs = c_on ? nxt : cur; // blend "self"
+    const float* ys = b_on ? cur : nxt; // blend "other"
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        x[k] = xs[SE_ARR + 8 * k + fi];
+        y[k] = ys[SE_ARR + 8 * k + fi];
+    }
+    if (!c_on) x[P_AMP] = 0.0f; // b.copy_silent().blend(b, alpha)   :911
+    if (!b_on) y[P_AMP] = 0.0f; // c.blend(c.copy_silent(), alpha)   :920
+}
+
+__device__ __forceinline__ FormantSeg load_formant_seg(const float* ue, uint32_t p, uint32_t n_elems, int fi)
+{
+    float x[6], y[6], bl;
+    seg_endpoints(ue, p, n_elems, fi, x, y, &bl);
+    FormantSeg s;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { s.x[k] = x[k]; s.d[k] = y[k] - x[k]; }
+    s.inv_bl = 1.0f / bl;
+    return s;
+}
+
+// tan(pi x) approximation of src/lib.rs:63-70, as numerator / denominator
+__device__ __forceinline__ void tan_nd(float x, float* num, float* den)
+{
+    const float p = fmaf(-x, x, x);      // (1 - x) x
+    const float q = fmaf(-x, x, 0.25f);  // (x + .5)(.5 - x)
+    *num = p * fmaf(-4.0f, q, 5.0f);
+    *den = q * fmaf(-4.0f, p, 5.0f);
+}
+
+// slowest natural decay (nepers per sample) of one formant's low-pass + SVF pair
+__device__ float decay_rate(float ff, float bw, float sm)
+{
+    float num, den;
+    tan_nd(ff, &num, &den);
+    const float g = num / den, k = bw / ff;
+    const float delta = 1.0f + g * (g + k);
+    const float det = (1.0f - g * k + g * g) / delta;   // product of the two SVF poles
+    const float htr = (1.0f - g * g) / delta;           // half trace
+    const float disc = htr * htr - det;
+    float rho = disc > 0.0f ? fabsf(htr) + sqrtf(disc) : sqrtf(fmaxf(det, 0.0f));
+    const float o = 1.0f - sm;
+    const float a5 = fabsf(o * o * o * o * o);          // low-pass pole :535
+    rho = fmaxf(rho, a5);
+    if (!(rho < 1.0f)) return 0.0f;                     // no decay (or NaN): warm up from sample 0
+    return -logf(fmaxf(rho, 1e-30f));
+}
+
+__device__ float seg_decay_rate(const float* ue, uint32_t p, uint32_t n_elems, int fi, float dff)
+{
+    float x[6], y[6], bl;
+    seg_endpoints(ue, p, n_elems, fi, x, y, &bl);
+    float r = decay_rate(x[P_FF] - dff, x[P_BW], x[P_SM]);
+    r = fminf(r, decay_rate(x[P_FF] + dff, x[P_BW], x[P_SM]));
+    r = fminf(r, decay_rate(y[P_FF] - dff, y[P_BW], y[P_SM]));
+    r = fminf(r, decay_rate(y[P_FF] + dff, y[P_BW], y[P_SM]));
+    r = fminf(r, decay_rate(x[P_FF] - dff, y[P_BW], x[P_SM]));
+    r = fminf(r, decay_rate(y[P_FF] + dff, x[P_BW], y[P_SM]));
+    return 0.9f * r;
+}
+
+// samples of history needed before n0 so that a zero-state start has decayed by exp(-need)
+__device__ uint32_t warmup_len(const float* ue, const SegRec* segs, uint32_t n_elems, uint32_t n0, int fi, float dff,
+                               float need)
+{
+    uint32_t p = last_le(n_elems, [&](uint32_t i) { return segs[i].start; }, (int64_t)n0 - 1);
+    float acc = 0.0f;
+    uint32_t hi = n0;
+    for (;;) {
+        const uint32_t lo = segs[p].start;
+        const float rate = seg_decay_rate(ue, p, n_elems, fi, fabsf(dff));
+        const float span = (float)(hi - lo);
+        if (rate > 0.0f && acc + rate * span >= need) {
+            const float extra = ceilf((need - acc) / rate);
+            uint32_t w = (n0 - hi) + (uint32_t)fminf(extra, span);
+            w = (w + 7u) & ~7u;
+            return min(w, n0);
+        }
+        acc += rate * span;
+        hi = lo;
+        if (p == 0) return n0;
+        --p;
+    }
+}
+
+struct LaneState {
+    // clocks
+    float time, jph;
+    uint32_t p;
+    // noise streams
+    uint32_t s_noise, s_ff, s_amp;   // LCG states: synth noise, next formant_freq draw, next formant_amp draw
+    uint32_t jw;                      // jitter wraps so far
+    float ffc, ffd, ampc, ampd;       // value-noise current and (next - current)
+    // filters
+    float a, b, c;
+};
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) k_formant(PlanDev P, void* __restrict__ out, int format)
+{
+    __shared__ float part[NW][32][33];
+    __shared__ unsigned long long row_out[32];
+    __shared__ uint32_t row_len[32];
+
+    const int lane = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5;
+    const uint32_t item_id = blockIdx.x * 32u + lane;
+    const bool have = item_id < P.n_items;
+    ItemDev it;
+    it.utt = 0; it.n0 = 0; it.len = 0; it.pad = 0;
+    if (have) it = P.items[item_id];
+    const UttDev& U = P.utts[it.utt];
+    const int fi = (have && (uint32_t)w < U.n_active) ? (int)U.active[w] : -1;
+    const bool on = fi >= 0 && it.len > 0;
+    if (w == 0) {
+        row_out[lane] = U.out_off + it.n0;
+        row_len[lane] = it.len;
+    }
+    const float* ue = P.elems + (size_t)U.elem_first * SEQ_WORDS;
+    const SegRec* segs = P.segs + U.elem_first;
+    const uint32_t n_elems = U.n_elems;
+    const uint32_t CL = P.chunk_len;
+
+    const float dt = sdiv(1.0f, U.voice.sample_rate);
+    const float ndt = -dt;
+    const float jinc = U.voice.jitter_frequency;
+    const float dff = U.voice.jitter_delta_formant_frequency;
+    const float hda = 0.5f * U.voice.jitter_delta_amplitude;   // :769
+    const float one_m_hda = 1.0f - hda;
+
+    // ---- warm-up depth: per lane, then the warp maximum so the whole warp walks the same rows
+    uint32_t wlen = 0;
+    if (on && it.n0 > 0) wlen = warmup_len(ue, segs, n_elems, it.n0, fi, dff, P.warmup_nepers);
+    uint32_t wmax = wlen;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    const uint32_t wmine = min(wmax, it.n0);      // multiple of 8 (n0 is a multiple of 32)
+    const uint32_t ns = it.n0 - wmine;            // first sample this lane computes
+
+    // ---- lane state at sample ns
+    LaneState st;
+    FormantSeg seg;
+    uint32_t lcg8a, lcg8c;
+    lcg_pow(8, &lcg8a, &lcg8c);
+    st.a = st.b = st.c = 0.0f;
+    st.time = 0.0f; st.jph = 0.0f; st.p = 0; st.jw = 0;
+    st.s_noise = st.s_ff = st.s_amp = 0;
+    st.ffc = st.ffd = st.ampc = st.ampd = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { seg.x[k] = 0.0f; seg.d[k] = 0.0f; }
+    seg.inv_bl = 0.0f;
+    if (on) {
+        st.p = last_le(n_elems, [&](uint32_t i) { return segs[i].start; }, (int64_t)ns);
+        st.time = clock_desc_run(segs[st.p].time0, dt, ns - segs[st.p].start).x;
+        seg = load_formant_seg(ue, st.p, n_elems, fi);
+        const JitSchedDev& JS = P.jscheds[U.jit_sched];
+        const JitRec* recs = P.jrecs + JS.rec_first;
+        st.jw = last_le(JS.n_recs, [&](uint32_t i) { return recs[i].n; }, (int64_t)ns);
+        st.jph = clock_asc_run(recs[st.jw].phase, jinc, (uint64_t)((int64_t)ns - recs[st.jw].n)).x;
+        const uint32_t seed = U.voice.jitter_seed;
+        const float c0 = lcg_float(lcg_jump(seed, jit_arr_cur_idx(0, fi, st.jw)));
+        st.s_ff = lcg_jump(seed, jit_arr_next_idx(0, fi, st.jw));
+        st.ffc = c0; st.ffd = lcg_float(st.s_ff) - c0;
+        const float c1 = lcg_float(lcg_jump(seed, jit_arr_cur_idx(1, fi, st.jw)));
+        st.s_amp = lcg_jump(seed, jit_arr_next_idx(1, fi, st.jw));
+        st.ampc = c1; st.ampd = lcg_float(st.s_amp) - c1;
+        st.s_noise = lcg_jump(U.voice.synth_seed, ns);   // noise of sample n is draw n+1  (:528)
+    }
+
+    // one sample of this lane's formant; returns v1 (band-pass output, :566)
+    auto sample = [&](float saw) -> float {
+        const float alpha = fminf(st.time * seg.inv_bl, 1.0f);               // :899
+        st.s_noise = st.s_noise * LCG_A + LCG_C;                             // :40
+        const float nz = fmaf(__uint_as_float((st.s_noise >> 9) | 0x3F800000u), 2.0f, -3.0f);
+        // parameters: Sequencer blend (:404-414) then Jitter (:764-773)
+        const float n1 = fmaf(st.jph, st.ffd, st.ffc);
+        const float n2 = fmaf(st.jph, st.ampd, st.ampc);
+        const float ff = fmaf(n1, dff, fmaf(alpha, seg.d[P_FF], seg.x[P_FF]));
+        const float bw = fmaf(alpha, seg.d[P_BW], seg.x[P_BW]);
+        const float sm = fmaf(alpha, seg.d[P_SM], seg.x[P_SM]);
+        const float br = fmaf(alpha, seg.d[P_BR], seg.x[P_BR]);
+        const float tb = fmaf(alpha, seg.d[P_TB], seg.x[P_TB]);
+        const float amp = fmaf(alpha, seg.d[P_AMP], seg.x[P_AMP]) * fmaf(n2, -hda, one_m_hda);
+        // source: breath mix, one-pole low-pass, turbulence, amplitude (:531-550)
+        const float nw = fmaf(br, nz - saw, saw);
+        const float o = 1.0f - sm, o2 = o * o;
+        const float a5 = o2 * o2 * o;                                        // exp_approx :75-82
+        st.a = fmaf(1.0f - a5, nw - st.a, st.a);                             // :538
+        const float v0 = st.a * fmaf(tb, nz - 1.0f, 1.0f) * amp;             // :544-550
+        // SVF coefficients (:555-562)
+        float num, den;
+        tan_nd(ff, &num, &den);
+        const float g = num * frcp(den);
+        const float k = bw * frcp(ff);
+        const float a1 = frcp(fmaf(g, g + k, 1.0f));
+        const float a2 = g * a1;
+        const float a3 = g * a2;
+        // SVF tick (:565-571)
+        const float v3 = v0 - st.c;
+        const float v1 = fmaf(a1, st.b, a2 * v3);
+        const float v2 = fmaf(a3, v3, fmaf(a2, st.b, st.c));
+        st.b = fmaf(2.0f, v1, -st.b);
+        st.c = fmaf(2.0f, v2, -st.c);
+        return v1;
+    };
+    // clock advance with the rare events handled (phoneme hand-over, value-noise wrap)
+    auto advance_slow = [&]() {
+        st.time = __fadd_rn(st.time, ndt);                                   // :861
+        if (st.time < 0.0f) {                                                // :864
+            ++st.p;
+            if (st.p < n_elems) {
+                st.time = __fadd_rn(st.time, ue[(size_t)st.p * SEQ_WORDS + SE_LEN]);   // :873
+                seg = load_formant_seg(ue, st.p, n_elems, fi);
+            }
+        }
+        st.jph = __fadd_rn(st.jph, jinc);                                    // :291
+        if (st.jph > 1.0f) {                                                 // :294
+            st.jph = __fadd_rn(st.jph, -1.0f);
+            ++st.jw;
+            const float nf = lcg_float(st.s_ff), na = lcg_float(st.s_amp);   // old next becomes current
+            if (st.jw == 1) {
+                st.s_ff = lcg_jump(U.voice.jitter_seed, jit_arr_next_idx(0, fi, 1));
+                st.s_amp = lcg_jump(U.voice.jitter_seed, jit_arr_next_idx(1, fi, 1));
+            } else {
+                st.s_ff = lcg8a * st.s_ff + lcg8c;                           // 8 draws per wrap :301
+                st.s_amp = lcg8a * st.s_amp + lcg8c;
+            }
+            st.ffc = nf; st.ffd = lcg_float(st.s_ff) - nf;
+            st.ampc = na; st.ampd = lcg_float(st.s_amp) - na;
+        }
+    };
+    // 8 consecutive samples; v[] receives v1 per sample
+    auto block8 = [&](const float* saw8, float* v) {
+        const bool quiet = (st.time > 9.0f * dt) && (st.jph + 9.0f * jinc < 1.0f);
+        if (quiet) { // no hand-over and no wrap can fall inside: branch-free literal clocks
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                v[k] = sample(saw8[k]);
+                st.time = __fadd_rn(st.time, ndt);
+                st.jph = __fadd_rn(st.jph, jinc);
+            }
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < 8; ++k) {
+                v[k] = sample(saw8[k]);
+                advance_slow();
+            }
+        }
+    };
+
+    // ---- warm-up: [n0 - wmax, n0) in steps of 8, no output
+    for (uint32_t r = wmax; r > 0; r -= 8) {
+        if (on && r <= wmine) {
+            const uint32_t n = it.n0 - r;                 // absolute sample, multiple of 8
+            const uint32_t src_item = U.item_first + n / CL;
+            const float4* sp = reinterpret_cast<const float4*>(P.saw + saw_index(src_item, n % CL, CL));
+            const float4 sa = __ldg(sp), sb = __ldg(sp + 1);
+            const float saw8[8] = { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w };
+            float v[8];
+            block8(saw8, v);
+        }
+    }
+
+    __syncthreads();
+    uint32_t lmax = 0;
+#pragma unroll 1
+    for (int r = 0; r < 32; ++r) lmax = max(lmax, row_len[r]);
+    const float4* sp = reinterpret_cast<const float4*>(P.saw + saw_index(item_id, 0, CL));
+
+    // ---- main: batches of 32 samples, CTA-wide formant sum + coalesced row stores
+    for (uint32_t base = 0; base < lmax; base += 32) {
+#pragma unroll 1
+        for (int s8 = 0; s8 < 4; ++s8) {
+            const uint32_t r = base + s8 * 8;
+            float v[8];
+            if (on && r < it.len) {
+                const float4 sa = __ldg(sp + (size_t)(r >> 3) * 64), sb = __ldg(sp + (size_t)(r >> 3) * 64 + 1);
+                const float saw8[8] = { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w };
+                block8(saw8, v);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) part[w][lane][s8 * 8 + k] = v[k];
+        }
+        __syncthreads();
+        // rows w, w+NW, ...: sum the formants in index order (Array::sum is a left fold, :123) and scale (:574)
+        for (int row = w; row < 32; row += NW) {
+            const uint32_t rl = row_len[row];
+            if (base + lane < rl) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int f = 0; f < NW; ++f) acc += part[f][row][lane];
+                acc *= 0.5f;
+                const unsigned long long o = row_out[row] + base + lane;
+                if (format == GRAIL_F32) {
+                    reinterpret_cast<float*>(out)[o] = acc;
+                } else {
+                    // (x * i16::MAX as f32) as i16: truncating, saturating, NaN -> 0 (examples/cli.rs:50)
+                    const float sc = acc * 32767.0f;
+                    int q = (sc != sc) ? 0 : __float2int_rz(fminf(fmaxf(sc, -32768.0f), 32767.0f));
+                    reinterpret_cast<short*>(out)[o] = (short)q;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Roofline probes: dense FFMA issue rate and MUFU.RCP rate of this device.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_probe_ffma(float* sink, int iters, float seed)
+{
+    float a0 = seed + threadIdx.x, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
+          a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f, c = 0.001f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+            a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+        }
+    }
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+__global__ void __launch_bounds__(256) k_probe_mufu(float* sink, int iters, float seed)
+{
+    float a0 = seed + 1.5f + threadIdx.x, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { a0 = frcp(a0); a1 = frcp(a1); a2 = frcp(a2); a3 = frcp(a3); }
+    }
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3;
+}
+
+} // namespace grail

@@ -1,0 +1,856 @@
+// grail_runtime.cu -- host runtime and C ABI (include/grail_cuda.h) of the B200 waveform path.
+//
+// Host side of the cut: exact per-phoneme schedule (the Sequencer's f32 clock in closed form), work
+// planning (time chunks x active formants), device memory, launches, transfers.  "Phoneme scheduling
+// stays on the host" (north_star); everything per-sample runs in grail_kernels.cuh.
+// Product code: no CPU synthesis path exists here -- without a device every compute entry point fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "grail_kernels.cuh"
+
+using namespace grail;
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct PoolBuf {
+    void*  ptr;
+    size_t size;
+    bool   in_use;
+};
+
+struct grail_ctx {
+    int            device = 0;
+    cudaStream_t   stream = nullptr;
+    cudaDeviceProp prop{};
+    std::string    err;
+    std::vector<PoolBuf> pool;
+    // options
+    double   warmup_nepers = 16.1;
+    uint32_t target_items = 0;      // 0 = one resident wave of k_formant CTAs
+    uint32_t min_chunk = 2048;
+    uint32_t max_chunk = 1u << 22;
+    int      debug_taps = 0;
+    // pinned staging for pageable D2H
+    void*    stage[2] = { nullptr, nullptr };
+    size_t   stage_bytes = 0;
+    cudaEvent_t stage_ev[2] = { nullptr, nullptr };
+};
+
+static int set_err(grail_ctx* ctx, int status, const char* fmt, ...)
+{
+    if (ctx) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        ctx->err = buf;
+    }
+    return status;
+}
+
+#define CU(ctx, call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return set_err((ctx), e_ == cudaErrorMemoryAllocation ? GRAIL_ERR_OOM : GRAIL_ERR_CUDA, \
+                           "%s failed: %s", #call, cudaGetErrorString(e_));                        \
+    } while (0)
+
+static int pool_alloc(grail_ctx* ctx, size_t bytes, void** out)
+{
+    if (bytes == 0) bytes = 256;
+    bytes = (bytes + 255) & ~(size_t)255;
+    int best = -1;
+    for (size_t i = 0; i < ctx->pool.size(); ++i) {
+        PoolBuf& b = ctx->pool[i];
+        if (!b.in_use && b.size >= bytes && b.size <= bytes * 2 + (1u << 20))
+            if (best < 0 || b.size < ctx->pool[best].size) best = (int)i;
+    }
+    if (best >= 0) {
+        ctx->pool[best].in_use = true;
+        *out = ctx->pool[best].ptr;
+        return GRAIL_OK;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        // drop cached free buffers and retry once
+        for (auto& b : ctx->pool)
+            if (!b.in_use && b.ptr) { cudaFree(b.ptr); b.ptr = nullptr; b.size = 0; }
+        ctx->pool.erase(std::remove_if(ctx->pool.begin(), ctx->pool.end(), [](const PoolBuf& b) { return !b.ptr; }),
+                        ctx->pool.end());
+        cudaGetLastError();
+        e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return set_err(ctx, GRAIL_ERR_OOM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        }
+    }
+    ctx->pool.push_back({ p, bytes, true });
+    *out = p;
+    return GRAIL_OK;
+}
+
+static void pool_free(grail_ctx* ctx, void* p)
+{
+    if (!p) return;
+    for (auto& b : ctx->pool)
+        if (b.ptr == p) { b.in_use = false; return; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+struct grail_plan {
+    grail_ctx* ctx = nullptr;
+    uint32_t n_utts = 0, n_elems = 0, n_items = 0, n_groups = 0, n_jscheds = 0, n_jrecs = 0, nw = 1;
+    uint32_t chunk_len = 0;
+    uint64_t total_samples = 0, f_words = 0, saw_words = 0;
+    std::vector<UttDev>      utts;       // host copies (original utterance order)
+    std::vector<ItemDev>     items;
+    std::vector<JitSchedDev> jscheds;
+    std::vector<SegRec>      segs;
+    std::vector<uint64_t>    out_offsets;
+    // device
+    float* d_elems = nullptr; SegRec* d_segs = nullptr; UttDev* d_utts = nullptr; ItemDev* d_items = nullptr;
+    JitSchedDev* d_jscheds = nullptr; JitRec* d_jrecs = nullptr; float* d_F = nullptr; float* d_saw = nullptr;
+    float* d_phase_dbg = nullptr; uint32_t* d_err = nullptr;
+    void* d_out = nullptr; size_t d_out_bytes = 0; int d_out_format = -1;
+    cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+    bool launched = false;
+    uint32_t last_launches = 0;
+};
+
+// exact Sequencer schedule of one utterance (reference src/lib.rs:859-888): per phoneme the index of its
+// first sample and the clock value there; returns the sample count, or <0 on unsupported input.
+struct SeqKey {
+    uint32_t t, len, dt;
+    bool operator==(const SeqKey& o) const { return t == o.t && len == o.len && dt == o.dt; }
+};
+struct SeqKeyHash {
+    size_t operator()(const SeqKey& k) const
+    {
+        uint64_t h = (uint64_t)k.t * 0x9E3779B97F4A7C15ull ^ ((uint64_t)k.len << 32 | k.dt);
+        h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+        return (size_t)h;
+    }
+};
+struct SeqVal { uint64_t steps; uint32_t x; };
+typedef std::unordered_map<SeqKey, SeqVal, SeqKeyHash> SeqCache;
+
+static const uint64_t MAX_UTT_SAMPLES = (1ull << 31) - 4096;
+
+static int64_t schedule_utterance(const grail_seq_elem* e, uint32_t n_elems, float sample_rate, SegRec* segs,
+                                  SeqCache& cache)
+{
+    const float dt = sdiv(1.0f, sample_rate);       // src/lib.rs:944
+    float t_neg = ssub(0.0f, dt);                   // first call: time = 0 - delta_time  (:861)
+    uint64_t n = 0;
+    for (uint32_t p = 0; p < n_elems; ++p) {
+        const float len = e[p].length;
+        const float time0 = sadd(t_neg, len);       // :873 / :882
+        if (segs) { segs[p].start = (uint32_t)n; segs[p].time0 = time0; }
+        const SeqKey key = { f2u(time0), 0u, f2u(dt) };
+        auto itc = cache.find(key);
+        SeqVal v;
+        if (itc != cache.end()) {
+            v = itc->second;
+        } else {
+            const ClockRun r = clock_desc_run(time0, dt, MAX_UTT_SAMPLES + 1);
+            if (r.stuck || !(r.x < 0.0f)) return -1; // clock cannot reach zero: the reference would never end
+            v.steps = r.steps;
+            v.x = f2u(r.x);
+            if (cache.size() < (1u << 20)) cache.emplace(key, v);
+        }
+        n += v.steps;
+        if (n > MAX_UTT_SAMPLES) return -1;
+        t_neg = u2f(v.x);
+    }
+    return (int64_t)n;
+}
+
+static int validate_inputs(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_t* utt_offsets,
+                           const grail_voice_params* voices, uint32_t n_utts)
+{
+    if (!utt_offsets || !voices || (n_utts && !elems && utt_offsets[n_utts] != 0))
+        return set_err(ctx, GRAIL_ERR_INVALID_ARG, "null input pointer");
+    for (uint32_t u = 0; u < n_utts; ++u) {
+        if (utt_offsets[u + 1] < utt_offsets[u])
+            return set_err(ctx, GRAIL_ERR_INVALID_ARG, "utt_offsets not monotone at %u", u);
+        const grail_voice_params& v = voices[u];
+        if (!(v.sample_rate > 0.0f) || !std::isfinite(v.sample_rate))
+            return set_err(ctx, GRAIL_ERR_INVALID_ARG, "utterance %u: sample_rate must be finite and > 0", u);
+        const float dt = sdiv(1.0f, v.sample_rate);
+        if (!std::isnormal(dt))
+            return set_err(ctx, GRAIL_ERR_INVALID_ARG, "utterance %u: 1/sample_rate is not a normal f32", u);
+        if (!(v.jitter_frequency >= 0.0f && v.jitter_frequency <= 0.25f))
+            return set_err(ctx, GRAIL_ERR_UNSUPPORTED,
+                           "utterance %u: jitter_frequency %g outside the supported range [0, 0.25]", u,
+                           (double)v.jitter_frequency);
+        if (!std::isfinite(v.jitter_delta_frequency) || !std::isfinite(v.jitter_delta_formant_frequency) ||
+            !std::isfinite(v.jitter_delta_amplitude))
+            return set_err(ctx, GRAIL_ERR_INVALID_ARG, "utterance %u: non-finite jitter scalar", u);
+        for (uint32_t p = utt_offsets[u]; p < utt_offsets[u + 1]; ++p)
+            if (!std::isfinite(elems[p].length))
+                return set_err(ctx, GRAIL_ERR_INVALID_ARG, "utterance %u: non-finite phoneme length", u);
+    }
+    return GRAIL_OK;
+}
+
+template <int NW>
+static void launch_formant(const PlanDev& P, void* out, int format, cudaStream_t s)
+{
+    k_formant<NW><<<P.n_groups, NW * 32, 0, s>>>(P, out, format);
+}
+template <int NW>
+static int formant_occupancy()
+{
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_formant<NW>, NW * 32, 0);
+    return nb;
+}
+static int formant_occupancy_nw(int nw)
+{
+    switch (nw) {
+    case 1: return formant_occupancy<1>();
+    case 2: return formant_occupancy<2>();
+    case 3: return formant_occupancy<3>();
+    case 4: return formant_occupancy<4>();
+    case 5: return formant_occupancy<5>();
+    case 6: return formant_occupancy<6>();
+    case 7: return formant_occupancy<7>();
+    default: return formant_occupancy<8>();
+    }
+}
+
+static PlanDev plan_dev(const grail_plan* pl, bool with_dbg)
+{
+    PlanDev P;
+    P.elems = pl->d_elems; P.segs = pl->d_segs; P.utts = pl->d_utts; P.items = pl->d_items;
+    P.jscheds = pl->d_jscheds; P.jrecs = pl->d_jrecs; P.F = pl->d_F; P.saw = pl->d_saw;
+    P.phase_dbg = with_dbg ? pl->d_phase_dbg : nullptr;
+    P.err = pl->d_err;
+    P.n_utts = pl->n_utts; P.n_items = pl->n_items; P.n_groups = pl->n_groups; P.n_jscheds = pl->n_jscheds;
+    P.chunk_len = pl->chunk_len;
+    P.warmup_nepers = (float)pl->ctx->warmup_nepers;
+    return P;
+}
+
+static void plan_release(grail_plan* pl)
+{
+    if (!pl) return;
+    grail_ctx* ctx = pl->ctx;
+    void* bufs[] = { pl->d_elems, pl->d_segs, pl->d_utts, pl->d_items, pl->d_jscheds, pl->d_jrecs, pl->d_F, pl->d_saw,
+                     pl->d_phase_dbg, pl->d_err, pl->d_out };
+    for (void* b : bufs) pool_free(ctx, b);
+    for (auto& e : pl->ev)
+        if (e) cudaEventDestroy(e);
+    delete pl;
+}
+
+static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_t* utt_offsets,
+                      const grail_voice_params* voices, uint32_t n_utts, grail_plan** out_plan)
+{
+    int rc = validate_inputs(ctx, elems, utt_offsets, voices, n_utts);
+    if (rc) return rc;
+    CU(ctx, cudaSetDevice(ctx->device));
+    grail_plan* pl = new (std::nothrow) grail_plan();
+    if (!pl) return set_err(ctx, GRAIL_ERR_OOM, "host allocation failed");
+    pl->ctx = ctx;
+    pl->n_utts = n_utts;
+    pl->n_elems = n_utts ? utt_offsets[n_utts] : 0;
+    pl->utts.resize(n_utts);
+    pl->segs.resize(pl->n_elems ? pl->n_elems : 1);
+    pl->out_offsets.assign(n_utts + 1, 0);
+
+    // ---- exact schedule + active formants
+    SeqCache cache;
+    std::unordered_map<uint32_t, uint32_t> jmap;
+    uint32_t nw = 1;
+    uint64_t total = 0, f_words = 0;
+    uint32_t n_max = 0;
+    for (uint32_t u = 0; u < n_utts; ++u) {
+        UttDev& U = pl->utts[u];
+        memset(&U, 0, sizeof U);
+        U.elem_first = utt_offsets[u];
+        U.n_elems = utt_offsets[u + 1] - utt_offsets[u];
+        const grail_seq_elem* e = elems + U.elem_first;
+        const int64_t n = schedule_utterance(e, U.n_elems, voices[u].sample_rate, pl->segs.data() + U.elem_first, cache);
+        if (n < 0) {
+            plan_release(pl);
+            return set_err(ctx, GRAIL_ERR_UNSUPPORTED,
+                           "utterance %u: more than %llu samples or a phoneme clock that never reaches zero", u,
+                           (unsigned long long)MAX_UTT_SAMPLES);
+        }
+        U.n_samples = (uint32_t)n;
+        U.voice = voices[u];
+        U.init_phase = 0.0f;
+        U.out_off = total;
+        U.f_off = f_words;
+        total += (uint64_t)n;
+        f_words += ((uint64_t)n + 7) & ~7ull;
+        n_max = std::max(n_max, U.n_samples);
+        pl->out_offsets[u + 1] = total;
+        // a formant whose amplitude is zero in every element contributes exactly 0 (v0 = 0 keeps the SVF at rest)
+        for (int i = 0; i < NF; ++i) {
+            bool act = false;
+            for (uint32_t p = 0; p < U.n_elems && !act; ++p)
+                act = e[p].has_elem && !(e[p].elem.formant_amp[i] == 0.0f);
+            if (act) U.active[U.n_active++] = (uint8_t)i;
+        }
+        nw = std::max(nw, U.n_active);
+        // jitter schedules are shared by every utterance with the same increment
+        const uint32_t key = f2u(voices[u].jitter_frequency);
+        auto jt = jmap.find(key);
+        if (jt == jmap.end()) {
+            JitSchedDev js;
+            memset(&js, 0, sizeof js);
+            js.inc = voices[u].jitter_frequency;
+            js.n_max = U.n_samples;
+            jmap.emplace(key, (uint32_t)pl->jscheds.size());
+            U.jit_sched = (uint32_t)pl->jscheds.size();
+            pl->jscheds.push_back(js);
+        } else {
+            U.jit_sched = jt->second;
+            pl->jscheds[jt->second].n_max = std::max(pl->jscheds[jt->second].n_max, U.n_samples);
+        }
+    }
+    pl->total_samples = total;
+    pl->f_words = f_words + 8;
+    pl->nw = nw;
+    uint64_t n_jrecs = 0;
+    for (auto& js : pl->jscheds) {
+        js.rec_first = (uint32_t)n_jrecs;
+        js.rec_cap = (uint32_t)((double)js.n_max * (double)js.inc * 1.01) + 8;
+        n_jrecs += js.rec_cap;
+    }
+    if (n_jrecs > 0xFFFFFFF0ull) {
+        plan_release(pl);
+        return set_err(ctx, GRAIL_ERR_UNSUPPORTED, "jitter schedule too large");
+    }
+    pl->n_jscheds = (uint32_t)pl->jscheds.size();
+    pl->n_jrecs = (uint32_t)n_jrecs;
+
+    // ---- chunking: aim for one resident wave of k_formant CTAs (32 chunks each)
+    uint64_t target = ctx->target_items;
+    if (target == 0) {
+        int occ = formant_occupancy_nw((int)nw);
+        if (occ < 1) occ = 1;
+        target = (uint64_t)ctx->prop.multiProcessorCount * (uint64_t)occ * 32ull;
+    }
+    uint64_t cl = (total + target - 1) / std::max<uint64_t>(target, 1);
+    cl = std::max<uint64_t>(cl, ctx->min_chunk);
+    cl = std::min<uint64_t>(cl, ctx->max_chunk);
+    cl = std::min<uint64_t>(cl, std::max<uint32_t>(n_max, 32u));
+    cl = (cl + 31) & ~31ull;
+    pl->chunk_len = (uint32_t)cl;
+
+    // ---- work items: utterances in descending length so a CTA's 32 chunks are of similar size
+    std::vector<uint32_t> order(n_utts);
+    for (uint32_t u = 0; u < n_utts; ++u) order[u] = u;
+    std::stable_sort(order.begin(), order.end(),
+                     [&](uint32_t a, uint32_t b) { return pl->utts[a].n_samples > pl->utts[b].n_samples; });
+    for (uint32_t u : order) {
+        UttDev& U = pl->utts[u];
+        U.item_first = (uint32_t)pl->items.size();
+        for (uint32_t n0 = 0; n0 < U.n_samples; n0 += pl->chunk_len) {
+            ItemDev it;
+            it.utt = u; it.n0 = n0; it.len = std::min(pl->chunk_len, U.n_samples - n0); it.pad = 0;
+            pl->items.push_back(it);
+        }
+        U.n_items = (uint32_t)pl->items.size() - U.item_first;
+    }
+    pl->n_items = (uint32_t)pl->items.size();
+    pl->n_groups = (pl->n_items + 31) / 32;
+    pl->saw_words = (uint64_t)pl->n_groups * 32ull * pl->chunk_len;
+
+    // ---- device buffers
+    auto fail = [&](int code) { plan_release(pl); return code; };
+#define PA(ptr, bytes)                                                         \
+    do {                                                                       \
+        void* p_ = nullptr;                                                    \
+        int rc_ = pool_alloc(ctx, (bytes), &p_);                               \
+        if (rc_) return fail(rc_);                                             \
+        (ptr) = reinterpret_cast<decltype(ptr)>(p_);                           \
+    } while (0)
+#define CUF(call)                                                                              \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            set_err(ctx, GRAIL_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));      \
+            return fail(GRAIL_ERR_CUDA);                                                       \
+        }                                                                                      \
+    } while (0)
+    PA(pl->d_elems, (size_t)std::max<uint32_t>(pl->n_elems, 1) * sizeof(grail_seq_elem) + 256);
+    PA(pl->d_segs, pl->segs.size() * sizeof(SegRec));
+    PA(pl->d_utts, std::max<size_t>(n_utts, 1) * sizeof(UttDev));
+    PA(pl->d_items, std::max<size_t>(pl->n_items, 1) * sizeof(ItemDev));
+    PA(pl->d_jscheds, std::max<size_t>(pl->n_jscheds, 1) * sizeof(JitSchedDev));
+    PA(pl->d_jrecs, std::max<size_t>(pl->n_jrecs, 1) * sizeof(JitRec));
+    PA(pl->d_F, pl->f_words * sizeof(float));
+    PA(pl->d_saw, std::max<uint64_t>(pl->saw_words, 8) * sizeof(float));
+    PA(pl->d_err, 256);
+    cudaStream_t s = ctx->stream;
+    if (pl->n_elems) CUF(cudaMemcpyAsync(pl->d_elems, elems, (size_t)pl->n_elems * sizeof(grail_seq_elem), cudaMemcpyHostToDevice, s));
+    CUF(cudaMemcpyAsync(pl->d_segs, pl->segs.data(), pl->segs.size() * sizeof(SegRec), cudaMemcpyHostToDevice, s));
+    if (n_utts) CUF(cudaMemcpyAsync(pl->d_utts, pl->utts.data(), n_utts * sizeof(UttDev), cudaMemcpyHostToDevice, s));
+    if (pl->n_items) CUF(cudaMemcpyAsync(pl->d_items, pl->items.data(), pl->n_items * sizeof(ItemDev), cudaMemcpyHostToDevice, s));
+    if (pl->n_jscheds) CUF(cudaMemcpyAsync(pl->d_jscheds, pl->jscheds.data(), pl->n_jscheds * sizeof(JitSchedDev), cudaMemcpyHostToDevice, s));
+    for (auto& e : pl->ev) CUF(cudaEventCreate(&e));
+    // the host vectors are read by the async copies above: make them safe to outlive this call
+    CUF(cudaStreamSynchronize(s));
+#undef PA
+#undef CUF
+    *out_plan = pl;
+    return GRAIL_OK;
+}
+
+static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, bool formant)
+{
+    grail_ctx* ctx = pl->ctx;
+    if (format != GRAIL_F32 && format != GRAIL_I16) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "unknown sample format");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const PlanDev P = plan_dev(pl, with_dbg);
+    pl->last_launches = 0;
+    CU(ctx, cudaMemsetAsync(pl->d_err, 0, 4, s));
+    CU(ctx, cudaEventRecord(pl->ev[0], s));
+    if (pl->n_items) {
+        k_jitter_schedule<<<(pl->n_jscheds + 63) / 64, 64, 0, s>>>(P);
+        pl->last_launches++;
+    }
+    CU(ctx, cudaEventRecord(pl->ev[1], s));
+    if (pl->n_items) {
+        const uint32_t runs = (pl->chunk_len + FREQ_RUN - 1) / FREQ_RUN;
+        const uint64_t threads = (uint64_t)pl->n_items * runs;
+        k_frequency<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(P, runs);
+        pl->last_launches++;
+    }
+    CU(ctx, cudaEventRecord(pl->ev[2], s));
+    if (pl->n_items) {
+        k_phase_serial<<<(pl->n_utts + 31) / 32, 32, 0, s>>>(P);
+        pl->last_launches++;
+    }
+    CU(ctx, cudaEventRecord(pl->ev[3], s));
+    if (pl->n_items && formant) {
+        switch (pl->nw) {
+        case 1: launch_formant<1>(P, d_out, format, s); break;
+        case 2: launch_formant<2>(P, d_out, format, s); break;
+        case 3: launch_formant<3>(P, d_out, format, s); break;
+        case 4: launch_formant<4>(P, d_out, format, s); break;
+        case 5: launch_formant<5>(P, d_out, format, s); break;
+        case 6: launch_formant<6>(P, d_out, format, s); break;
+        case 7: launch_formant<7>(P, d_out, format, s); break;
+        default: launch_formant<8>(P, d_out, format, s); break;
+        }
+        pl->last_launches++;
+    }
+    CU(ctx, cudaEventRecord(pl->ev[4], s));
+    CU(ctx, cudaGetLastError());
+    pl->launched = true;
+    return GRAIL_OK;
+}
+
+static int plan_check_device_errors(grail_plan* pl)
+{
+    grail_ctx* ctx = pl->ctx;
+    uint32_t e = 0;
+    CU(ctx, cudaMemcpyAsync(&e, pl->d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (e & DEV_ERR_JIT_OVERFLOW) return set_err(ctx, GRAIL_ERR_CUDA, "device: jitter schedule overflow");
+    if (e) return set_err(ctx, GRAIL_ERR_CUDA, "device error word 0x%x", e);
+    return GRAIL_OK;
+}
+
+static size_t format_bytes(int format) { return format == GRAIL_I16 ? 2 : 4; }
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int grail_cuda_abi_version(void) { return GRAIL_ABI_VERSION; }
+
+int grail_cuda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char* grail_cuda_status_string(int status)
+{
+    switch (status) {
+    case GRAIL_OK: return "ok";
+    case GRAIL_ERR_INVALID_ARG: return "invalid argument";
+    case GRAIL_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU path)";
+    case GRAIL_ERR_CUDA: return "CUDA error";
+    case GRAIL_ERR_OOM: return "out of memory";
+    case GRAIL_ERR_COUNT_MISMATCH: return "output offsets disagree with the exact sample counts";
+    case GRAIL_ERR_UNSUPPORTED: return "input outside the supported domain";
+    default: return "unknown status";
+    }
+}
+
+int grail_cuda_create(int device, grail_ctx** out_ctx)
+{
+    if (!out_ctx) return GRAIL_ERR_INVALID_ARG;
+    *out_ctx = nullptr;
+    int n = grail_cuda_device_count();
+    if (n <= 0 || device < 0 || device >= n) return GRAIL_ERR_NO_DEVICE;
+    grail_ctx* ctx = new (std::nothrow) grail_ctx();
+    if (!ctx) return GRAIL_ERR_OOM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        delete ctx;
+        return GRAIL_ERR_CUDA;
+    }
+    if (ctx->prop.major < 10) {
+        // built for sm_100a only; an older device cannot run the cubin
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return GRAIL_ERR_NO_DEVICE;
+    }
+    *out_ctx = ctx;
+    return GRAIL_OK;
+}
+
+void grail_cuda_destroy(grail_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->pool)
+        if (b.ptr) cudaFree(b.ptr);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
+        if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+    }
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* grail_cuda_last_error(const grail_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+void* grail_cuda_stream_handle(grail_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int grail_cuda_synchronize(grail_ctx* ctx)
+{
+    if (!ctx) return GRAIL_ERR_INVALID_ARG;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return GRAIL_OK;
+}
+
+int grail_cuda_set_option(grail_ctx* ctx, const char* key, double value)
+{
+    if (!ctx || !key) return GRAIL_ERR_INVALID_ARG;
+    if (!strcmp(key, "warmup_nepers")) {
+        if (!(value >= 0.0 && value <= 200.0)) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "warmup_nepers out of range");
+        ctx->warmup_nepers = value;
+    } else if (!strcmp(key, "target_lanes")) {
+        ctx->target_items = value < 0 ? 0u : (uint32_t)value;
+    } else if (!strcmp(key, "min_chunk")) {
+        ctx->min_chunk = std::max(32u, (uint32_t)value);
+    } else if (!strcmp(key, "max_chunk")) {
+        ctx->max_chunk = std::max(32u, (uint32_t)value);
+    } else if (!strcmp(key, "debug_taps")) {
+        ctx->debug_taps = value != 0.0;
+    } else {
+        return set_err(ctx, GRAIL_ERR_INVALID_ARG, "unknown option '%s'", key);
+    }
+    return GRAIL_OK;
+}
+
+int grail_cuda_host_alloc(grail_ctx* ctx, size_t bytes, void** out_ptr)
+{
+    if (!ctx || !out_ptr) return GRAIL_ERR_INVALID_ARG;
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaHostAlloc(out_ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(ctx, GRAIL_ERR_OOM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return GRAIL_OK;
+}
+
+void grail_cuda_host_free(grail_ctx* ctx, void* ptr)
+{
+    (void)ctx;
+    if (ptr) cudaFreeHost(ptr);
+}
+
+int grail_cuda_count_samples(const grail_seq_elem* elems, const uint32_t* utt_offsets,
+                             const grail_voice_params* voices, uint32_t n_utts, uint64_t* counts)
+{
+    if (!counts) return GRAIL_ERR_INVALID_ARG;
+    int rc = validate_inputs(nullptr, elems, utt_offsets, voices, n_utts);
+    if (rc) return rc;
+    SeqCache cache;
+    for (uint32_t u = 0; u < n_utts; ++u) {
+        const int64_t n = schedule_utterance(elems + utt_offsets[u], utt_offsets[u + 1] - utt_offsets[u],
+                                             voices[u].sample_rate, nullptr, cache);
+        if (n < 0) return GRAIL_ERR_UNSUPPORTED;
+        counts[u] = (uint64_t)n;
+    }
+    return GRAIL_OK;
+}
+
+int grail_cuda_plan_create(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_t* utt_offsets,
+                           const grail_voice_params* voices, uint32_t n_utts, grail_plan** out_plan)
+{
+    if (!ctx || !out_plan) return GRAIL_ERR_INVALID_ARG;
+    *out_plan = nullptr;
+    return plan_build(ctx, elems, utt_offsets, voices, n_utts, out_plan);
+}
+
+void grail_cuda_plan_destroy(grail_plan* plan)
+{
+    if (!plan) return;
+    cudaSetDevice(plan->ctx->device);
+    cudaStreamSynchronize(plan->ctx->stream);
+    plan_release(plan);
+}
+
+uint64_t grail_cuda_plan_total_samples(const grail_plan* plan) { return plan ? plan->total_samples : 0; }
+
+int grail_cuda_plan_out_offsets(const grail_plan* plan, uint64_t* out_offsets)
+{
+    if (!plan || !out_offsets) return GRAIL_ERR_INVALID_ARG;
+    memcpy(out_offsets, plan->out_offsets.data(), plan->out_offsets.size() * sizeof(uint64_t));
+    return GRAIL_OK;
+}
+
+int grail_cuda_plan_launch(grail_plan* plan, void* d_out, int format)
+{
+    if (!plan) return GRAIL_ERR_INVALID_ARG;
+    if (!d_out && plan->total_samples) return set_err(plan->ctx, GRAIL_ERR_INVALID_ARG, "null output pointer");
+    return plan_enqueue(plan, d_out, format, false, true);
+}
+
+int grail_cuda_plan_device_output(grail_plan* plan, int format, void** out_dptr)
+{
+    if (!plan || !out_dptr) return GRAIL_ERR_INVALID_ARG;
+    grail_ctx* ctx = plan->ctx;
+    const size_t need = (size_t)std::max<uint64_t>(plan->total_samples, 1) * format_bytes(format);
+    if (!plan->d_out || plan->d_out_bytes < need) {
+        if (plan->d_out) {
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            pool_free(ctx, plan->d_out);
+            plan->d_out = nullptr;
+        }
+        int rc = pool_alloc(ctx, need, &plan->d_out);
+        if (rc) return rc;
+        plan->d_out_bytes = need;
+    }
+    plan->d_out_format = format;
+    *out_dptr = plan->d_out;
+    return GRAIL_OK;
+}
+
+int grail_cuda_plan_read_output(grail_plan* plan, int format, void* host_out)
+{
+    if (!plan || (!host_out && plan->total_samples)) return GRAIL_ERR_INVALID_ARG;
+    grail_ctx* ctx = plan->ctx;
+    if (!plan->d_out || plan->d_out_format != format)
+        return set_err(ctx, GRAIL_ERR_INVALID_ARG, "plan has no device output in this format; launch into "
+                                                   "grail_cuda_plan_device_output first");
+    const size_t bytes = (size_t)plan->total_samples * format_bytes(format);
+    if (bytes) CU(ctx, cudaMemcpyAsync(host_out, plan->d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return plan_check_device_errors(plan);
+}
+
+int grail_cuda_plan_timings(const grail_plan* plan, grail_timings* out)
+{
+    if (!plan || !out) return GRAIL_ERR_INVALID_ARG;
+    memset(out, 0, sizeof *out);
+    if (!plan->launched) return GRAIL_OK;
+    grail_ctx* ctx = plan->ctx;
+    CU(ctx, cudaEventSynchronize(plan->ev[4]));
+    CU(ctx, cudaEventElapsedTime(&out->schedule_ms, plan->ev[0], plan->ev[1]));
+    CU(ctx, cudaEventElapsedTime(&out->frequency_ms, plan->ev[1], plan->ev[2]));
+    CU(ctx, cudaEventElapsedTime(&out->phase_ms, plan->ev[2], plan->ev[3]));
+    CU(ctx, cudaEventElapsedTime(&out->formant_ms, plan->ev[3], plan->ev[4]));
+    CU(ctx, cudaEventElapsedTime(&out->total_ms, plan->ev[0], plan->ev[4]));
+    out->n_launches = plan->last_launches;
+    return GRAIL_OK;
+}
+
+int grail_cuda_plan_read_intermediates(grail_plan* plan, float* frequency, float* carrier_phase, float* saw)
+{
+    if (!plan) return GRAIL_ERR_INVALID_ARG;
+    grail_ctx* ctx = plan->ctx;
+    if (!plan->d_phase_dbg) {
+        void* p = nullptr;
+        int rc = pool_alloc(ctx, plan->f_words * sizeof(float), &p);
+        if (rc) return rc;
+        plan->d_phase_dbg = (float*)p;
+    }
+    int rc = plan_enqueue(plan, nullptr, GRAIL_F32, true, false);
+    if (rc) return rc;
+    rc = plan_check_device_errors(plan);
+    if (rc) return rc;
+    std::vector<float> tmp(std::max<uint64_t>(plan->f_words, plan->saw_words));
+    auto gather_linear = [&](const float* dsrc, float* dst) -> int {
+        CU(ctx, cudaMemcpy(tmp.data(), dsrc, plan->f_words * sizeof(float), cudaMemcpyDeviceToHost));
+        for (uint32_t u = 0; u < plan->n_utts; ++u) {
+            const UttDev& U = plan->utts[u];
+            memcpy(dst + U.out_off, tmp.data() + U.f_off, (size_t)U.n_samples * sizeof(float));
+        }
+        return GRAIL_OK;
+    };
+    if (frequency && (rc = gather_linear(plan->d_F, frequency))) return rc;
+    if (carrier_phase && (rc = gather_linear(plan->d_phase_dbg, carrier_phase))) return rc;
+    if (saw) {
+        CU(ctx, cudaMemcpy(tmp.data(), plan->d_saw, plan->saw_words * sizeof(float), cudaMemcpyDeviceToHost));
+        const uint32_t CL = plan->chunk_len;
+        for (uint32_t u = 0; u < plan->n_utts; ++u) {
+            const UttDev& U = plan->utts[u];
+            for (uint32_t n = 0; n < U.n_samples; ++n) {
+                const uint32_t item = U.item_first + n / CL, j = n % CL;
+                const size_t idx = ((size_t)(item >> 5) * (CL >> 3) + (j >> 3)) * 256u + (item & 31u) * 8u + (j & 7u);
+                saw[U.out_off + n] = tmp[idx];
+            }
+        }
+    }
+    return GRAIL_OK;
+}
+
+int grail_cuda_synthesize_batch(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_t* utt_offsets,
+                                const grail_voice_params* voices, uint32_t n_utts, float* out,
+                                const uint64_t* out_offsets, int out_is_device)
+{
+    if (!ctx) return GRAIL_ERR_INVALID_ARG;
+    if (!out_offsets) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "null out_offsets");
+    grail_plan* pl = nullptr;
+    int rc = plan_build(ctx, elems, utt_offsets, voices, n_utts, &pl);
+    if (rc) return rc;
+    // the caller's layout must be the exact counts, packed in utterance order from out_offsets[0]
+    for (uint32_t u = 0; u < n_utts; ++u) {
+        if (out_offsets[u + 1] - out_offsets[u] != (uint64_t)pl->utts[u].n_samples || out_offsets[u + 1] < out_offsets[u]) {
+            const unsigned long long want = pl->utts[u].n_samples, got = out_offsets[u + 1] - out_offsets[u];
+            plan_release(pl);
+            return set_err(ctx, GRAIL_ERR_COUNT_MISMATCH, "utterance %u yields %llu samples, out_offsets leave room for %llu",
+                           u, want, got);
+        }
+    }
+    if (pl->total_samples && !out) {
+        plan_release(pl);
+        return set_err(ctx, GRAIL_ERR_INVALID_ARG, "null output pointer");
+    }
+    float* base = out ? out + out_offsets[0] : nullptr;
+    if (out_is_device) {
+        rc = plan_enqueue(pl, base, GRAIL_F32, false, true);
+        if (!rc) rc = plan_check_device_errors(pl);
+    } else {
+        void* d = nullptr;
+        rc = grail_cuda_plan_device_output(pl, GRAIL_F32, &d);
+        if (!rc) rc = plan_enqueue(pl, d, GRAIL_F32, false, true);
+        if (!rc) rc = grail_cuda_plan_read_output(pl, GRAIL_F32, base);
+    }
+    cudaStreamSynchronize(ctx->stream);
+    plan_release(pl);
+    return rc;
+}
+
+// ---- streaming: declared in the ABI; the carried-state kernels land in a later milestone ----------
+int grail_cuda_stream_new(grail_ctx* ctx, const grail_voice_params* voice, grail_stream** out_stream)
+{
+    (void)voice;
+    if (out_stream) *out_stream = nullptr;
+    return set_err(ctx, GRAIL_ERR_UNSUPPORTED, "streaming is not implemented in this build");
+}
+int grail_cuda_stream_push(grail_stream* s, const grail_seq_elem* elems, uint32_t n_elems)
+{
+    (void)s; (void)elems; (void)n_elems;
+    return GRAIL_ERR_UNSUPPORTED;
+}
+int grail_cuda_stream_finish(grail_stream* s) { (void)s; return GRAIL_ERR_UNSUPPORTED; }
+int grail_cuda_stream_pull(grail_stream* s, float* out, uint64_t max_samples, uint64_t* n_written)
+{
+    (void)s; (void)out; (void)max_samples;
+    if (n_written) *n_written = 0;
+    return GRAIL_ERR_UNSUPPORTED;
+}
+void grail_cuda_stream_free(grail_stream* s) { (void)s; }
+
+// ---- roofline probes ---------------------------------------------------------------------------
+int grail_cuda_probe_fp32_peak(grail_ctx* ctx, double* ffma_flops, double* mufu_ops, double* sm_mhz_effective)
+{
+    if (!ctx) return GRAIL_ERR_INVALID_ARG;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int blocks = ctx->prop.multiProcessorCount * 8, threads = 256;
+    float* sink = nullptr;
+    void* p = nullptr;
+    int rc = pool_alloc(ctx, (size_t)blocks * threads * sizeof(float), &p);
+    if (rc) return rc;
+    sink = (float*)p;
+    cudaEvent_t e0, e1;
+    CU(ctx, cudaEventCreate(&e0));
+    CU(ctx, cudaEventCreate(&e1));
+    cudaStream_t s = ctx->stream;
+    float ms = 0.f;
+    double best_f = 0, best_m = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        const int iters = 4096;
+        CU(ctx, cudaEventRecord(e0, s));
+        k_probe_ffma<<<blocks, threads, 0, s>>>(sink, iters, 1.0f);
+        CU(ctx, cudaEventRecord(e1, s));
+        CU(ctx, cudaEventSynchronize(e1));
+        CU(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = (double)blocks * threads * iters * 16.0 * 8.0 * 2.0 / (ms * 1e-3);
+        if (rep > 0) best_f = std::max(best_f, fl);
+        const int miters = 1024;
+        CU(ctx, cudaEventRecord(e0, s));
+        k_probe_mufu<<<blocks, threads, 0, s>>>(sink, miters, 1.0f);
+        CU(ctx, cudaEventRecord(e1, s));
+        CU(ctx, cudaEventSynchronize(e1));
+        CU(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        const double mo = (double)blocks * threads * miters * 16.0 * 4.0 / (ms * 1e-3);
+        if (rep > 0) best_m = std::max(best_m, mo);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    pool_free(ctx, sink);
+    if (ffma_flops) *ffma_flops = best_f;
+    if (mufu_ops) *mufu_ops = best_m;
+    if (sm_mhz_effective) // FFMA peak = SMs x 128 lanes x 2 flop x f  =>  the clock the probe actually ran at
+        *sm_mhz_effective = best_f / ((double)ctx->prop.multiProcessorCount * 128.0 * 2.0) * 1e-6;
+    return GRAIL_OK;
+}
+
+// ---- debug hooks for the exact-clock tests (host only) -------------------------------------------
+void grail_cuda_debug_clock_desc(float x, float d, uint64_t max_steps, float* x_out, uint64_t* steps, int* stuck)
+{
+    const ClockRun r = clock_desc_run(x, d, max_steps);
+    *x_out = r.x; *steps = r.steps; *stuck = r.stuck;
+}
+void grail_cuda_debug_clock_asc(float x, float d, uint64_t max_steps, float* x_out, uint64_t* steps, int* stuck)
+{
+    const ClockRun r = clock_asc_run(x, d, max_steps);
+    *x_out = r.x; *steps = r.steps; *stuck = r.stuck;
+}
+uint32_t grail_cuda_debug_lcg_jump(uint32_t seed, uint64_t n) { return lcg_jump(seed, n); }
+uint64_t grail_cuda_debug_jitter_index(int gen, int which /*0 cur, 1 next*/, int i, uint64_t w)
+{
+    if (gen < 0) return which ? jit_freq_next_idx(w) : jit_freq_cur_idx(w);
+    return which ? jit_arr_next_idx(gen, i, w) : jit_arr_cur_idx(gen, i, w);
+}
+
+} // extern "C"

@@ -1,0 +1,384 @@
+"""Host-side mirror of the reference's operator interface for the waveform path.
+
+Same names and argument meaning as reference src/lib.rs: SynthesisElem (:316-460), SequenceElem (:814-835),
+Voice (:696-717), and the iterator verbs `.sequence(voice)` (:936-953), `.jitter(seed, voice)` (:781-801),
+`.synthesize()` (:582-600).  `Sequencer` and `Jitter` are lazy descriptors; `Synthesize` drains the upstream
+SequenceElems on the host, runs the per-sample work on the B200 through the C ABI, and yields f32 samples.
+There is no CPU synthesis path in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field, replace
+from typing import Iterable, Iterator, Optional, Sequence
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import ELEM_DT, SEQ_ELEM_DT, VOICE_DT, GrailError, Timings, ptr
+
+f32 = np.float32
+NUM_FORMANTS = 8                 # src/lib.rs:24
+DEFAULT_SAMPLE_RATE = f32(44100.0)  # src/lib.rs:21
+
+
+def _arr(x) -> np.ndarray:
+    a = np.asarray(x, dtype=np.float32)
+    if a.shape != (NUM_FORMANTS,):
+        raise ValueError(f"expected {NUM_FORMANTS} formant values, got shape {a.shape}")
+    return a.copy()
+
+
+@dataclass
+class SynthesisElem:
+    """reference src/lib.rs:316-337; all frequencies normalised to the sample rate"""
+    frequency: np.float32
+    formant_freq: np.ndarray
+    formant_bw: np.ndarray
+    formant_smooth: np.ndarray
+    formant_breath: np.ndarray
+    formant_turb: np.ndarray
+    formant_amp: np.ndarray
+
+    @staticmethod
+    def new(sample_rate, frequency, formant_freq, formant_smooth, formant_bw, formant_breath, formant_turb,
+            formant_amp) -> "SynthesisElem":
+        """src/lib.rs:343-364 (note the reference's argument order: smooth before bw)"""
+        return SynthesisElem(f32(frequency), _arr(formant_freq), _arr(formant_bw), _arr(formant_smooth),
+                             _arr(formant_breath), _arr(formant_turb), _arr(formant_amp)).resample(1.0, sample_rate)
+
+    @staticmethod
+    def silent() -> "SynthesisElem":
+        """src/lib.rs:367-377"""
+        q, z = np.full(8, 0.25, f32), np.zeros(8, f32)
+        return SynthesisElem(f32(0.25), q.copy(), q.copy(), q.copy(), z.copy(), z.copy(), z.copy())
+
+    @staticmethod
+    def new_phoneme(formant_freq, formant_bw, formant_smooth, formant_turb, formant_breath, formant_amp) -> "SynthesisElem":
+        """src/lib.rs:381-401: amplitudes normalised by their sequential f32 sum, then resample(1, 44100)"""
+        amp = _arr(formant_amp)
+        s = f32(0.0)
+        for v in amp:               # Array::sum is a left fold (:123)
+            s = f32(s + v)
+        return SynthesisElem(f32(0.0), _arr(formant_freq), _arr(formant_bw), _arr(formant_smooth), _arr(formant_breath),
+                             _arr(formant_turb), (amp / s).astype(f32)).resample(1.0, DEFAULT_SAMPLE_RATE)
+
+    def blend(self, other: "SynthesisElem", alpha) -> "SynthesisElem":
+        """src/lib.rs:404-414"""
+        a = f32(alpha)
+        om = f32(f32(1.0) - a)
+        b = lambda x, y: (x * om + y * a).astype(f32)  # noqa: E731
+        return SynthesisElem(f32(f32(self.frequency * om) + f32(other.frequency * a)),
+                             b(self.formant_freq, other.formant_freq), b(self.formant_bw, other.formant_bw),
+                             b(self.formant_smooth, other.formant_smooth), b(self.formant_breath, other.formant_breath),
+                             b(self.formant_turb, other.formant_turb), b(self.formant_amp, other.formant_amp))
+
+    def resample(self, old_sample_rate, new_sample_rate) -> "SynthesisElem":
+        """src/lib.rs:418-440"""
+        scale = f32(f32(old_sample_rate) / f32(new_sample_rate))
+        ff = (self.formant_freq * scale).astype(f32)
+        return SynthesisElem(
+            f32(min(f32(self.frequency * scale), f32(0.5))),
+            np.minimum(ff, f32(0.5)).astype(f32),
+            (self.formant_bw * scale).astype(f32),
+            (self.formant_smooth * scale).astype(f32),
+            self.formant_breath.copy(), self.formant_turb.copy(),
+            np.where(ff > f32(0.5), f32(0.0), self.formant_amp).astype(f32))
+
+    def copy_with_frequency(self, frequency) -> "SynthesisElem":
+        """src/lib.rs:445-450"""
+        return replace(self, frequency=f32(min(f32(frequency), f32(0.5))))
+
+    def copy_silent(self) -> "SynthesisElem":
+        """src/lib.rs:454-459"""
+        return replace(self, formant_amp=np.zeros(8, f32))
+
+    def to_record(self) -> np.ndarray:
+        r = np.zeros((), ELEM_DT)
+        for k in ELEM_DT.names:
+            r[k] = getattr(self, k)
+        return r
+
+
+@dataclass
+class SequenceElem:
+    """reference src/lib.rs:814-835"""
+    elem: Optional[SynthesisElem]
+    length: np.float32
+    blend_length: np.float32
+
+    @staticmethod
+    def new(elem, length, blend_length) -> "SequenceElem":
+        return SequenceElem(elem, f32(length), f32(blend_length))
+
+
+@dataclass
+class Voice:
+    """reference src/lib.rs:696-717"""
+    sample_rate: np.float32
+    phonemes: "object"
+    center_frequency: np.float32
+    jitter_frequency: np.float32
+    jitter_delta_frequency: np.float32
+    jitter_delta_formant_frequency: np.float32
+    jitter_delta_amplitude: np.float32
+
+    def params(self, jitter_seed: int = 0, synth_seed: int = 0) -> np.ndarray:
+        """the grail_voice_params record crossing the C ABI"""
+        v = np.zeros((), VOICE_DT)
+        for k in ("sample_rate", "jitter_frequency", "jitter_delta_frequency", "jitter_delta_formant_frequency",
+                  "jitter_delta_amplitude"):
+            v[k] = getattr(self, k)
+        v["jitter_seed"] = jitter_seed & 0xFFFFFFFF
+        v["synth_seed"] = synth_seed & 0xFFFFFFFF
+        return v
+
+
+def pack_sequence(elems: Iterable[SequenceElem]) -> np.ndarray:
+    """SequenceElems -> grail_seq_elem records"""
+    lst = list(elems)
+    out = np.zeros(len(lst), SEQ_ELEM_DT)
+    for i, e in enumerate(lst):
+        out[i]["length"] = e.length
+        out[i]["blend_length"] = e.blend_length
+        if e.elem is not None:
+            out[i]["has_elem"] = 1
+            out[i]["elem"] = e.elem.to_record()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# device context / plans
+# ------------------------------------------------------------------------------------------------
+class Context:
+    """one CUDA device + stream (grail_ctx).  Raises GrailError(ERR_NO_DEVICE) without a GPU."""
+
+    def __init__(self, device: int = 0):
+        self._L = _ffi.lib()
+        h = C.c_void_p()
+        rc = self._L.grail_cuda_create(device, C.byref(h))
+        if rc:
+            raise GrailError(rc)
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.grail_cuda_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc:
+            raise GrailError(rc, self._L.grail_cuda_last_error(self._h).decode())
+
+    def set_option(self, key: str, value: float):
+        self._check(self._L.grail_cuda_set_option(self._h, key.encode(), float(value)))
+
+    def synchronize(self):
+        self._check(self._L.grail_cuda_synchronize(self._h))
+
+    @property
+    def stream_handle(self) -> int:
+        return int(self._L.grail_cuda_stream_handle(self._h) or 0)
+
+    def pinned_empty(self, n: int, dtype=np.float32) -> np.ndarray:
+        """a numpy array backed by page-locked host memory (freed with the context's process)"""
+        nbytes = int(n) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self._check(self._L.grail_cuda_host_alloc(self._h, max(nbytes, 1), C.byref(p)))
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(n))
+        arr._grail_pinned = p  # keep the address alive with the array object
+        return arr
+
+    def probe_fp32_peak(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._check(self._L.grail_cuda_probe_fp32_peak(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"ffma_flops": a.value, "mufu_ops": b.value, "sm_mhz_effective": c.value}
+
+    # -- one-shot (host buffers in, host buffer out): the drop-in for draining the iterator chain
+    def synthesize_batch(self, elems: np.ndarray, utt_offsets: np.ndarray, voices: np.ndarray,
+                         out: Optional[np.ndarray] = None, out_offsets: Optional[np.ndarray] = None):
+        e = np.ascontiguousarray(elems, SEQ_ELEM_DT)
+        offs = np.ascontiguousarray(utt_offsets, np.uint32)
+        v = np.ascontiguousarray(voices, VOICE_DT).reshape(-1)
+        n = len(offs) - 1
+        if len(v) != n:
+            raise ValueError("one grail_voice_params per utterance")
+        if out_offsets is None:
+            out_offsets = np.concatenate([[0], np.cumsum(count_samples(e, offs, v))]).astype(np.uint64)
+        oo = np.ascontiguousarray(out_offsets, np.uint64)
+        if out is None:
+            out = np.empty(int(oo[-1]), np.float32)
+        self._check(self._L.grail_cuda_synthesize_batch(self._h, ptr(e), ptr(offs), ptr(v), n, ptr(out), ptr(oo), 0))
+        return out, oo
+
+    def plan(self, elems: np.ndarray, utt_offsets: np.ndarray, voices: np.ndarray) -> "Plan":
+        return Plan(self, elems, utt_offsets, voices)
+
+
+class Plan:
+    """a batch resident in HBM (grail_plan): upload once, launch many times"""
+
+    def __init__(self, ctx: Context, elems, utt_offsets, voices):
+        self.ctx = ctx
+        self._L = ctx._L
+        e = np.ascontiguousarray(elems, SEQ_ELEM_DT)
+        offs = np.ascontiguousarray(utt_offsets, np.uint32)
+        v = np.ascontiguousarray(voices, VOICE_DT).reshape(-1)
+        self.n_utts = len(offs) - 1
+        h = C.c_void_p()
+        ctx._check(self._L.grail_cuda_plan_create(ctx._h, ptr(e), ptr(offs), ptr(v), self.n_utts, C.byref(h)))
+        self._h = h
+        self.total_samples = int(self._L.grail_cuda_plan_total_samples(h))
+        oo = np.zeros(self.n_utts + 1, np.uint64)
+        ctx._check(self._L.grail_cuda_plan_out_offsets(h, ptr(oo)))
+        self.out_offsets = oo
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            self._L.grail_cuda_plan_destroy(self._h)
+        self._h = None
+
+    __del__ = close
+
+    def device_output(self, fmt: int = _ffi.F32) -> int:
+        p = C.c_void_p()
+        self.ctx._check(self._L.grail_cuda_plan_device_output(self._h, fmt, C.byref(p)))
+        return int(p.value)
+
+    def launch(self, d_out: Optional[int] = None, fmt: int = _ffi.F32):
+        """enqueue the whole path on the ctx stream (asynchronous)"""
+        if d_out is None:
+            d_out = self.device_output(fmt)
+        self.ctx._check(self._L.grail_cuda_plan_launch(self._h, C.c_void_p(d_out), fmt))
+
+    def read_output(self, out: Optional[np.ndarray] = None, fmt: int = _ffi.F32) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.total_samples, np.float32 if fmt == _ffi.F32 else np.int16)
+        self.ctx._check(self._L.grail_cuda_plan_read_output(self._h, fmt, ptr(out)))
+        return out
+
+    def timings(self) -> dict:
+        t = Timings()
+        self.ctx._check(self._L.grail_cuda_plan_timings(self._h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in Timings._fields_}
+
+    def read_intermediates(self):
+        """bit-exact taps: (F_t, carrier phase before each sample, polyBLEP saw), packed like the output"""
+        n = self.total_samples
+        f, p, s = (np.zeros(n, np.float32) for _ in range(3))
+        self.ctx._check(self._L.grail_cuda_plan_read_intermediates(self._h, ptr(f), ptr(p), ptr(s)))
+        return f, p, s
+
+
+def count_samples(elems: np.ndarray, utt_offsets: np.ndarray, voices: np.ndarray) -> np.ndarray:
+    """exact f32-clock sample counts (host only; grail_cuda_count_samples)"""
+    L = _ffi.lib()
+    e = np.ascontiguousarray(elems, SEQ_ELEM_DT)
+    offs = np.ascontiguousarray(utt_offsets, np.uint32)
+    v = np.ascontiguousarray(voices, VOICE_DT).reshape(-1)
+    counts = np.zeros(len(offs) - 1, np.uint64)
+    rc = L.grail_cuda_count_samples(ptr(e), ptr(offs), ptr(v), len(offs) - 1, ptr(counts))
+    if rc:
+        raise GrailError(rc)
+    return counts
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+# ------------------------------------------------------------------------------------------------
+# the iterator verbs
+# ------------------------------------------------------------------------------------------------
+class Sequencer:
+    """`.sequence(voice)` (src/lib.rs:941-949): a lazy descriptor; nothing runs until `.synthesize()`"""
+
+    def __init__(self, upstream: Iterable[SequenceElem], voice: Voice):
+        self.upstream = upstream
+        self.voice = voice
+
+    def jitter(self, seed: int, voice: Voice) -> "Jitter":
+        return Jitter(self, seed, voice)
+
+    def synthesize(self, ctx: Optional[Context] = None) -> "Synthesize":
+        # no Jitter stage == a Jitter whose three deltas are zero (x + n*0 and a * (1 - d*0) are identities)
+        quiet = replace(self.voice, jitter_delta_frequency=f32(0), jitter_delta_formant_frequency=f32(0),
+                        jitter_delta_amplitude=f32(0))
+        return Synthesize(self, 0, quiet, ctx)
+
+
+class Jitter:
+    """`.jitter(seed, voice)` (src/lib.rs:786-797): lazy descriptor"""
+
+    def __init__(self, sequencer: Sequencer, seed: int, voice: Voice):
+        if not isinstance(sequencer, Sequencer):
+            raise TypeError("the GPU path takes `.sequence(voice).jitter(seed, voice).synthesize()`; an arbitrary "
+                            "Iterator<Item = SynthesisElem> cannot be lowered and there is no CPU path")
+        self.sequencer = sequencer
+        self.seed = seed
+        self.voice = voice
+
+    def synthesize(self, ctx: Optional[Context] = None) -> "Synthesize":
+        return Synthesize(self.sequencer, self.seed, self.voice, ctx)
+
+
+class Synthesize:
+    """`.synthesize()` (src/lib.rs:587-596): Iterator<Item = f32>.  The first `next()` drains the upstream
+    SequenceElems, synthesizes the whole utterance on the device and then yields from the buffer."""
+
+    def __init__(self, sequencer: Sequencer, seed: int, jitter_voice: Voice, ctx: Optional[Context]):
+        self.sequencer = sequencer
+        self.seed = seed
+        self.jitter_voice = jitter_voice
+        self.ctx = ctx
+        self._buf: Optional[np.ndarray] = None
+        self._pos = 0
+
+    def _run(self):
+        seq = pack_sequence(self.sequencer.upstream)
+        v = self.jitter_voice.params(self.seed, 0)
+        v["sample_rate"] = self.sequencer.voice.sample_rate  # the Sequencer's voice sets delta_time (:944)
+        ctx = self.ctx or default_context()
+        out, _ = ctx.synthesize_batch(seq, np.array([0, len(seq)], np.uint32), v.reshape(1))
+        self._buf = out
+
+    def collect(self) -> np.ndarray:
+        """the `Vec::extend(iterator)` of examples/cli.rs:175-184"""
+        if self._buf is None:
+            self._run()
+        out = self._buf[self._pos:]
+        self._pos = len(self._buf)
+        return out
+
+    def __iter__(self) -> Iterator[np.float32]:
+        return self
+
+    def __next__(self) -> np.float32:
+        if self._buf is None:
+            self._run()
+        if self._pos >= len(self._buf):
+            raise StopIteration
+        x = self._buf[self._pos]
+        self._pos += 1
+        return x
+
+
+def sequence(elems: Iterable[SequenceElem], voice: Voice) -> Sequencer:
+    """IntoSequencer::sequence (src/lib.rs:936-953)"""
+    return Sequencer(elems, voice)

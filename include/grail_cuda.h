@@ -1,0 +1,170 @@
+/*
+ * grail_cuda.h -- C ABI of the B200-native waveform-generation path of grail-rs.
+ *
+ * The library replaces exactly one piece of the reference: the per-sample iterator chain
+ *
+ *     <IntoIterator<Item = SequenceElem>>.sequence(voice).jitter(seed, voice).synthesize()
+ *
+ * (reference src/lib.rs:936-953 IntoSequencer::sequence, :781-801 IntoJitter::jitter,
+ *  :582-600 IntoSynthesize::synthesize, drained by examples/cli.rs:175-184).
+ * Everything above that cut (Transcriber, Intonator, Selector; per phoneme) stays on the host in
+ * the caller's language.  The reference has no FFI of its own; these entry points are what a
+ * `grail-cuda-sys` crate would bind (see INTEGRATION.md for the Rust declarations).
+ *
+ * Conventions: plain pointers and sizes, caller owns every buffer, every function returns a
+ * grail_status (0 = ok) and never unwinds.  There is NO CPU fallback: without a CUDA device
+ * grail_cuda_create fails with GRAIL_ERR_NO_DEVICE.  A ctx is used from one thread at a time.
+ */
+#ifndef GRAIL_CUDA_H
+#define GRAIL_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRAIL_NUM_FORMANTS 8 /* reference NUM_FORMANTS, src/lib.rs:24 */
+#define GRAIL_ABI_VERSION 1
+
+typedef enum grail_status {
+    GRAIL_OK = 0,
+    GRAIL_ERR_INVALID_ARG = 1,   /* null pointer, non-monotone offsets, non-finite scalar ... */
+    GRAIL_ERR_NO_DEVICE = 2,     /* no usable CUDA device (there is no CPU path) */
+    GRAIL_ERR_CUDA = 3,          /* a CUDA runtime call failed; see grail_cuda_last_error */
+    GRAIL_ERR_OOM = 4,           /* device or pinned-host allocation failed */
+    GRAIL_ERR_COUNT_MISMATCH = 5,/* out_offsets disagree with the exact f32-clock sample counts */
+    GRAIL_ERR_UNSUPPORTED = 6    /* input outside the supported domain (documented per call) */
+} grail_status;
+
+/* SynthesisElem, reference src/lib.rs:316-337 (same field order; Rust structs are not repr(C),
+ * the -sys crate converts).  All frequencies are normalised to the sample rate. */
+typedef struct grail_elem {
+    float frequency;
+    float formant_freq[GRAIL_NUM_FORMANTS];
+    float formant_bw[GRAIL_NUM_FORMANTS];
+    float formant_smooth[GRAIL_NUM_FORMANTS];
+    float formant_breath[GRAIL_NUM_FORMANTS];
+    float formant_turb[GRAIL_NUM_FORMANTS];
+    float formant_amp[GRAIL_NUM_FORMANTS];
+} grail_elem; /* 196 bytes */
+
+/* SequenceElem, reference src/lib.rs:814-824.  has_elem = 0 encodes elem: None (Silence / Stop /
+ * Glide, src/lib.rs:666); `elem` is then ignored. */
+typedef struct grail_seq_elem {
+    uint32_t   has_elem;
+    grail_elem elem;
+    float      length;       /* seconds */
+    float      blend_length; /* seconds */
+} grail_seq_elem; /* 208 bytes */
+
+/* The Voice scalars the hot path reads (reference src/lib.rs:696-717) plus the two seeds:
+ * jitter_seed is the `seed` argument of .jitter(seed, voice) (src/lib.rs:786); synth_seed is the
+ * Synthesize noise seed, which the reference hard-codes to 0 (src/lib.rs:594). */
+typedef struct grail_voice_params {
+    float    sample_rate;
+    float    jitter_frequency;
+    float    jitter_delta_frequency;
+    float    jitter_delta_formant_frequency;
+    float    jitter_delta_amplitude;
+    uint32_t jitter_seed;
+    uint32_t synth_seed;
+} grail_voice_params; /* 28 bytes */
+
+typedef struct grail_ctx grail_ctx;       /* one CUDA device + stream + scratch arena */
+typedef struct grail_plan grail_plan;     /* a batch resident in HBM, ready to launch */
+typedef struct grail_stream grail_stream; /* one unbounded utterance with carried state */
+
+/* Output sample encodings.  F32 is the reference's Iterator<Item = f32>; I16 is the WAV writer's
+ * `(x * i16::MAX as f32) as i16` saturating, truncating cast (examples/cli.rs:49-51). */
+typedef enum grail_sample_format { GRAIL_F32 = 0, GRAIL_I16 = 1 } grail_sample_format;
+
+/* Kernel-level timing of the most recent launch (CUDA events on the ctx stream), milliseconds. */
+typedef struct grail_timings {
+    float schedule_ms;  /* exact clock schedule (Sequencer time / jitter phase)        */
+    float frequency_ms; /* bit-exact per-sample fundamental F_t                         */
+    float phase_ms;     /* bit-exact carrier phase + polyBLEP saw                       */
+    float formant_ms;   /* noise, 8x low-pass, 8x SVF band-pass, sum: the dominant kernel */
+    float total_ms;     /* first launch to last launch, same stream                     */
+    uint32_t n_launches;/* kernels launched by that call                                */
+} grail_timings;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int grail_cuda_abi_version(void);
+/* number of CUDA devices visible to this process (0 if none / no driver) */
+int grail_cuda_device_count(void);
+const char* grail_cuda_status_string(int status);
+
+/* ---- context ------------------------------------------------------------------------------ */
+int  grail_cuda_create(int device, grail_ctx** out_ctx);
+void grail_cuda_destroy(grail_ctx* ctx);
+/* message of the last failing call on this ctx ("" if none); valid until the next call */
+const char* grail_cuda_last_error(const grail_ctx* ctx);
+/* the ctx's cudaStream_t as an opaque pointer (for event timing / interop) */
+void* grail_cuda_stream_handle(grail_ctx* ctx);
+int  grail_cuda_synchronize(grail_ctx* ctx);
+/* tuning knobs: "warmup_nepers" (float, filter warm-up depth, default 16.1 ~ 1e-7),
+ * "target_lanes" (int, time-chunks the planner aims for), "max_chunk" / "min_chunk" (samples) */
+int  grail_cuda_set_option(grail_ctx* ctx, const char* key, double value);
+
+/* pinned host memory for full-rate H2D/D2H (optional; pageable buffers also work) */
+int  grail_cuda_host_alloc(grail_ctx* ctx, size_t bytes, void** out_ptr);
+void grail_cuda_host_free(grail_ctx* ctx, void* ptr);
+
+/* ---- exact sample counts (host only, no device needed) --------------------------------------
+ * counts[u] = number of samples Sequencer yields for utterance u, i.e. the number of times the
+ * f32 clock `time -= 1/sample_rate` (src/lib.rs:861) stays non-negative, with the carried
+ * remainder of src/lib.rs:873,882.  Bit-exact; evaluated in closed form per binade.
+ * utt_offsets has n_utts+1 entries indexing `elems`. */
+int grail_cuda_count_samples(const grail_seq_elem* elems, const uint32_t* utt_offsets,
+                             const grail_voice_params* voices, uint32_t n_utts, uint64_t* counts);
+
+/* ---- one-shot batch synthesis (the drop-in for draining the iterator chain) ------------------
+ * elems / utt_offsets / voices are HOST pointers.  out receives utterance u at
+ * out[out_offsets[u] .. out_offsets[u+1]) (mono f32); out_offsets[u+1]-out_offsets[u] must equal
+ * the exact count, else GRAIL_ERR_COUNT_MISMATCH.  out is a host pointer (pinned or pageable)
+ * unless out_is_device != 0.  Blocks until the samples are in `out`. */
+int grail_cuda_synthesize_batch(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_t* utt_offsets,
+                                const grail_voice_params* voices, uint32_t n_utts, float* out,
+                                const uint64_t* out_offsets, int out_is_device);
+
+/* ---- resident plans (throughput path: inputs stay in HBM between launches) ------------------ */
+int  grail_cuda_plan_create(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_t* utt_offsets,
+                            const grail_voice_params* voices, uint32_t n_utts, grail_plan** out_plan);
+void grail_cuda_plan_destroy(grail_plan* plan);
+uint64_t grail_cuda_plan_total_samples(const grail_plan* plan);
+/* exact per-utterance offsets (n_utts+1 entries) of the plan's packed output */
+int  grail_cuda_plan_out_offsets(const grail_plan* plan, uint64_t* out_offsets);
+/* enqueue every kernel of the path on the ctx stream; d_out is a DEVICE pointer to
+ * total_samples elements of `format`.  Asynchronous: pair with grail_cuda_synchronize. */
+int  grail_cuda_plan_launch(grail_plan* plan, void* d_out, int format);
+/* the plan's own device output buffer (allocated on first use), for callers with no allocator */
+int  grail_cuda_plan_device_output(grail_plan* plan, int format, void** out_dptr);
+/* D2H of the packed output into a host buffer (chunked, through pinned staging if pageable) */
+int  grail_cuda_plan_read_output(grail_plan* plan, int format, void* host_out);
+int  grail_cuda_plan_timings(const grail_plan* plan, grail_timings* out);
+/* debug / parity taps, host buffers of total_samples entries; any may be NULL:
+ * the bit-exact fundamental F_t, the carrier phase BEFORE each sample, and the polyBLEP saw */
+int  grail_cuda_plan_read_intermediates(grail_plan* plan, float* frequency, float* carrier_phase, float* saw);
+
+/* ---- streaming (unbounded input, examples/interactive.rs:31-38) -----------------------------
+ * A grail_stream is the Copy-able state of the three iterators (Sequencer{cur,next,time},
+ * Jitter{3 generators}, Synthesize{phase, a, b, c, seed}).  push appends
+ * upstream SequenceElems; pull synthesizes up to max_samples more samples and returns how many
+ * were produced (fewer only when the upstream ran dry: the last pushed element is held back as
+ * `next` until another element or grail_cuda_stream_finish arrives). */
+int  grail_cuda_stream_new(grail_ctx* ctx, const grail_voice_params* voice, grail_stream** out_stream);
+int  grail_cuda_stream_push(grail_stream* s, const grail_seq_elem* elems, uint32_t n_elems);
+int  grail_cuda_stream_finish(grail_stream* s);
+int  grail_cuda_stream_pull(grail_stream* s, float* out, uint64_t max_samples, uint64_t* n_written);
+void grail_cuda_stream_free(grail_stream* s);
+
+/* ---- roofline probes (used by bench.py; device microbenchmarks, not part of the path) -------- */
+/* dense FFMA issue rate of this device, in FP32 flop/s (2 per FFMA), and MUFU.RCP rate in op/s */
+int grail_cuda_probe_fp32_peak(grail_ctx* ctx, double* ffma_flops, double* mufu_ops, double* sm_mhz_effective);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAIL_CUDA_H */

@@ -1,0 +1,213 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Bar (BASELINE.json north_star): sample counts, LCG/jitter stream, Sequencer clock, F_t, carrier phase and saw
+bit-exact; audio within max-abs 1e-4 and >= 90 dB SNR of the oracle's f32 output."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import grail_rs_b200 as g
+from grail_rs_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+MAX_ABS = 1e-4      # north_star tolerance
+MIN_SNR_DB = 90.0   # north_star tolerance
+KAT = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "survey_probe_kat.json")))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = g.Context(0)
+    yield c
+    c.close()
+
+
+def check_batch(ctx, oracle, elems, offs, vp, exact_taps=True, label=""):
+    """run the batch on the device and compare every utterance with the oracle; returns worst-case stats"""
+    plan = ctx.plan(elems, offs, vp)
+    plan.launch()
+    out = plan.read_output()
+    oo = plan.out_offsets
+    taps = plan.read_intermediates() if exact_taps else None
+    worst = {"max_abs": 0.0, "snr_db": float("inf")}
+    for u in range(len(offs) - 1):
+        e = elems[offs[u]:offs[u + 1]]
+        want, tr, _ = oracle.synthesize(e, vp[u], trace=exact_taps)
+        n = int(oo[u + 1] - oo[u])
+        assert n == len(want), f"{label} utt {u}: sample count {n} != oracle {len(want)}"
+        got = out[oo[u]:oo[u + 1]]
+        if exact_taps and n:
+            f, ph, saw = (t[oo[u]:oo[u + 1]] for t in taps)
+            assert np.array_equal(f.view(np.uint32), tr["frequency"].view(np.uint32)), f"{label} utt {u}: F_t not bit-exact"
+            assert np.array_equal(ph.view(np.uint32), tr["carrier_phase"].view(np.uint32)), f"{label} utt {u}: phase not bit-exact"
+        if n and np.any(want):
+            st = W.parity_stats(got, want)
+            assert st["max_abs"] <= MAX_ABS and st["snr_db"] >= MIN_SNR_DB, f"{label} utt {u}: {st}"
+            worst["max_abs"] = max(worst["max_abs"], st["max_abs"])
+            worst["snr_db"] = min(worst["snr_db"], st["snr_db"])
+        elif n:
+            assert not np.any(got), f"{label} utt {u}: oracle is silent, device is not"
+    plan.close()
+    return worst, out, oo
+
+
+@pytest.mark.parametrize("kat", [k for k in KAT["utterances"] if not k.get("slow")], ids=lambda k: k["name"])
+def test_kat_utterances(ctx, oracle, kat):
+    elems, offs, vp = W.from_phonemes([kat["phonemes"]], g.voices.generic(), [kat["jitter_seed"]])
+    worst, out, oo = check_batch(ctx, oracle, elems, offs, vp, label=kat["name"])
+    assert len(out) == kat["n"]
+    print(kat["name"], worst)
+
+
+@pytest.mark.parametrize("min_chunk,target", [(32, 1 << 20), (256, 1 << 16), (2048, 0), (1 << 22, 1)])
+def test_chunking_is_transparent(ctx, oracle, min_chunk, target):
+    """any time-chunking (from 32-sample chunks to one chunk per utterance) gives the same audio"""
+    ctx.set_option("min_chunk", min_chunk)
+    ctx.set_option("target_lanes", target)
+    try:
+        elems, offs, vp = W.from_phonemes([[0, 4, 3], [3, 0, 4, 4], [4]], g.voices.generic(), [1, 2, 3])
+        worst, _, _ = check_batch(ctx, oracle, elems, offs, vp, label=f"chunk{min_chunk}")
+        print(min_chunk, worst)
+    finally:
+        ctx.set_option("min_chunk", 2048)
+        ctx.set_option("target_lanes", 0)
+
+
+def test_edge_cases(ctx, oracle):
+    v = g.voices.generic()
+    lists = [[], [3], [0], [0, 1, 2], [0, 0, 0, 3], [3, 0, 0, 4], [4, 3]]
+    elems, offs, vp = W.from_phonemes(lists, v, list(range(len(lists))))
+    elems = elems.copy()
+    # ragged lengths, a phoneme shorter than one sample, zero blend length
+    elems["length"][offs[5]:offs[6]] = np.array([0.3, 1e-6, 0.011, 0.25], np.float32)
+    elems["blend_length"][offs[6]] = 0.0
+    elems["blend_length"][offs[4] + 3] = 0.05
+    worst, out, oo = check_batch(ctx, oracle, elems, offs, vp, label="edge")
+    assert oo[1] == 0                      # empty utterance yields nothing
+    print(worst)
+
+
+def test_empty_batch(ctx):
+    out, oo = ctx.synthesize_batch(np.zeros(0, g.SEQ_ELEM_DT), np.zeros(1, np.uint32), np.zeros(0, g.VOICE_DT))
+    assert len(out) == 0 and oo.tolist() == [0]
+
+
+@pytest.mark.parametrize("rate", [16000.0, 22050.0, 48000.0])
+def test_sample_rate_sweep(ctx, oracle, rate):
+    """config 5 shape at small size: the voice rebuilt per rate; counts per SURVEY 8d"""
+    elems, offs, vp = W.config2(3, 10, sample_rate=rate)
+    worst, out, oo = check_batch(ctx, oracle, elems, offs, vp, label=f"rate{rate}")
+    assert int(oo[1]) == KAT["sample_rate_counts"][str(int(rate))][2]
+    print(rate, worst)
+
+
+def test_random_voices(ctx, oracle):
+    """config 4 distribution at small size: 8 active formants, random pitch / bandwidths / jitter"""
+    for rate in (44100.0, 16000.0):
+        elems, offs, vp = W.config4(24, sample_rate=rate)
+        worst, _, _ = check_batch(ctx, oracle, elems, offs, vp, label=f"cfg4@{rate}")
+        print(rate, worst)
+
+
+def test_random_voices_chunked(ctx, oracle):
+    """the same with forced short chunks: exercises the warm-up bound on high-Q random resonators"""
+    ctx.set_option("min_chunk", 1024)
+    ctx.set_option("target_lanes", 1 << 20)
+    try:
+        elems, offs, vp = W.config4(16, sample_rate=44100.0, first_utt=100)
+        worst, _, _ = check_batch(ctx, oracle, elems, offs, vp, label="cfg4-chunked")
+        print(worst)
+    finally:
+        ctx.set_option("min_chunk", 2048)
+        ctx.set_option("target_lanes", 0)
+
+
+def test_iterator_chain_drop_in(ctx, oracle):
+    """the reference's own call shape (examples/cli.rs:175-184) through the mirrored verbs"""
+    v = g.voices.generic()
+    lang = g.languages.generic()
+    audio = (g.transcribe("a pie i oui e a", lang).intonate(lang, v).select(v)
+             .sequence(v).jitter(0, v).synthesize(ctx).collect())
+    ph = [int(p) for p in g.transcribe("a pie i oui e a", lang)]
+    want, _, _ = oracle.synthesize(oracle.select(ph, oracle.generic_voice()), oracle.voice_params(oracle.generic_voice(), 0))
+    assert len(audio) == len(want)
+    st = W.parity_stats(audio, want)
+    assert st["max_abs"] <= MAX_ABS and st["snr_db"] >= MIN_SNR_DB, st
+    it = g.sequence([g.SequenceElem.new(v.phonemes.a.copy_with_frequency(v.center_frequency), 0.01, 0.01)], v).jitter(3, v).synthesize(ctx)
+    first = [next(it) for _ in range(5)]
+    assert len(first) == 5 and len(first + list(it)) in (440, 441)
+
+
+def test_i16_output(ctx, oracle):
+    elems, offs, vp = W.from_phonemes([[0, 3, 4]], g.voices.generic(), [5])
+    plan = ctx.plan(elems, offs, vp)
+    plan.launch(fmt=g.I16)
+    pcm = plan.read_output(fmt=g.I16)
+    want, _, _ = oracle.synthesize(elems, vp[0])
+    ref = np.trunc(want.astype(np.float32) * np.float32(32767.0)).astype(np.int16)   # examples/cli.rs:50
+    assert len(pcm) == len(ref) and np.abs(pcm.astype(np.int32) - ref.astype(np.int32)).max() <= 4
+    plan.close()
+
+
+def test_count_mismatch_is_reported(ctx):
+    elems, offs, vp = W.from_phonemes([[0, 3]], g.voices.generic(), [0])
+    bad = np.array([0, 44100], np.uint64)
+    with pytest.raises(g.GrailError) as ei:
+        ctx.synthesize_batch(elems, offs, vp, out=np.zeros(44100, np.float32), out_offsets=bad)
+    assert ei.value.status == g._ffi.ERR_COUNT_MISMATCH
+
+
+def test_relaunch_is_deterministic(ctx):
+    elems, offs, vp = W.config2(8, 4)
+    plan = ctx.plan(elems, offs, vp)
+    plan.launch()
+    a = plan.read_output().copy()
+    plan.launch()
+    b = plan.read_output()
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    t = plan.timings()
+    assert t["n_launches"] == 4 and t["total_ms"] > 0
+    plan.close()
+
+
+def test_properties_the_author_left_empty(ctx, oracle):
+    """synthesize_normalized / jitter_within_bounds (src/lib.rs:603-608, 804-805) as real property tests"""
+    elems, offs, vp = W.config2(16, 6)
+    out, oo = ctx.synthesize_batch(elems, offs, vp)
+    assert np.isfinite(out).all() and np.abs(out).max() <= 1.0        # peak values don't exceed 1.0
+    plan = ctx.plan(elems, offs, vp)
+    plan.launch()
+    f, ph, saw = plan.read_intermediates()
+    cf, dj = float(g.voices.generic().center_frequency), float(g.voices.generic().jitter_delta_frequency)
+    voiced = f[f < 0.2]
+    assert voiced.min() >= cf - dj * 1.0001 and voiced.max() <= cf + dj * 1.0001   # jitter stays inside its bounds
+    assert ph.min() >= 0.0 and ph.max() < 1.0
+    plan.close()
+
+
+def test_full_size_config2_properties(ctx, oracle):
+    """BASELINE config 2 at full size: exact counts, a spot-check of utterances against the oracle, and
+    size-independent properties (same phonemes + same seed => identical audio; different seed => different)"""
+    elems, offs, vp = W.config2(1024, 10)
+    vp = vp.copy()
+    ph = W.config2_phonemes(1024, 10)
+    twin = next(u for u in range(1, 1024) if ph[u] == ph[0])
+    vp["jitter_seed"][twin] = vp["jitter_seed"][0]
+    plan = ctx.plan(elems, offs, vp)
+    assert plan.total_samples == 1024 * 220476
+    plan.launch()
+    out = plan.read_output()
+    oo = plan.out_offsets
+    assert np.isfinite(out).all()
+    assert np.array_equal(out[oo[0]:oo[1]].view(np.uint32), out[oo[twin]:oo[twin + 1]].view(np.uint32))
+    other = next(u for u in range(1, 1024) if ph[u] == ph[0] and u != twin)
+    assert not np.array_equal(out[oo[0]:oo[1]], out[oo[other]:oo[other + 1]])
+    for u in (0, 1, 511, 1023):
+        want, _, _ = oracle.synthesize(elems[offs[u]:offs[u + 1]], vp[u])
+        st = W.parity_stats(out[oo[u]:oo[u + 1]], want)
+        assert st["max_abs"] <= MAX_ABS and st["snr_db"] >= MIN_SNR_DB, (u, st)
+    print(plan.timings())
+    plan.close()
