@@ -195,7 +195,7 @@ GRAIL_HD ClockRun clock_desc_run(float x, float d, uint64_t max_steps)
             if (S != 0 && m > 0x800001u) {
                 // every in-binade step needs m_prev - S >= 2^23 + 1 (then the exact difference is
                 // still inside this binade, so the rounding grid is u)
-                uint64_t k = (uint64_t)(m - 0x800001u) / S;
+                uint64_t k = (m - 0x800001u) / S;   // 32-bit divide
                 if (k > max_steps - r.steps) k = max_steps - r.steps;
                 if (k > 0) {
                     const uint32_t m2 = m - (uint32_t)(k * S);
@@ -238,7 +238,7 @@ GRAIL_HD ClockRun clock_asc_run(float x, float d, uint64_t max_steps)
             const uint32_t S = clock_binade_step(m, ex, md, ed);
             if (S != 0 && m < 0xFFFFFFu) {
                 // m_prev + S <= 2^24 - 1 keeps the exact sum below 2^(e+1): grid u, no wrap (x < 1)
-                uint64_t k = (uint64_t)(0xFFFFFFu - m) / S;
+                uint64_t k = (0xFFFFFFu - m) / S;   // 32-bit divide
                 if (k > max_steps - r.steps) k = max_steps - r.steps;
                 if (k > 0) {
                     const uint32_t m2 = m + (uint32_t)(k * S);
@@ -273,5 +273,31 @@ struct JitRec {          // one per jitter period (value-noise wrap), shared by 
     int32_t  n;          // sample at which this period's wrap happened (-1 for the initial period)
     float    phase;      // value-noise phase after that sample (0 for the initial period)
 };
+
+
+// Wrap schedule of one value-noise phase clock over samples [0, n_max): rec[w] = {sample of the w-th wrap,
+// phase after it}; rec[0] is the initial period.  Returns the number of records, or 0 if `cap` is too small.
+// Shared by the host planner (few schedules) and k_jitter_schedule (many).
+GRAIL_HD uint32_t jitter_schedule_walk(float inc, uint32_t n_max, JitRec* rec, uint32_t cap)
+{
+    if (cap == 0) return 0;
+    int64_t n = -1;
+    float ph = 0.0f;
+    uint32_t w = 0;
+    rec[0].n = -1;
+    rec[0].phase = 0.0f;
+    const int64_t last = (int64_t)n_max - 1;
+    while (n < last) {
+        const ClockRun r = clock_asc_run(ph, inc, (uint64_t)(last - n));
+        n += (int64_t)r.steps;
+        if (r.stuck || !(r.x > 1.0f)) break;
+        ph = ssub(r.x, 1.0f); // src/lib.rs:246
+        ++w;
+        if (w >= cap) return 0;
+        rec[w].n = (int32_t)n;
+        rec[w].phase = ph;
+    }
+    return w + 1;
+}
 
 } // namespace grail

@@ -2,7 +2,7 @@
 //
 //   k_jitter_schedule  exact wrap schedule of the value-noise phase clock      (src/lib.rs:242-251)
 //   k_frequency        bit-exact per-sample fundamental F_t                     (src/lib.rs:861-931, 753-763)
-//   k_phase_serial     bit-exact carrier phase + polyBLEP saw, one lane/utt     (src/lib.rs:503-525)
+//   k_phase_warp       bit-exact carrier phase + polyBLEP saw, one warp/utt     (src/lib.rs:503-525)
 //   k_formant<NW>      noise, low-pass, turbulence, SVF band-pass, formant sum  (src/lib.rs:528-577, 764-773)
 //
 // Exactness classes: the clocks, the LCG streams, F_t, the carrier phase and the saw are
@@ -105,30 +105,14 @@ __global__ void k_jitter_schedule(PlanDev P)
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P.n_jscheds) return;
     JitSchedDev& S = P.jscheds[s];
-    JitRec* rec = P.jrecs + S.rec_first;
-    const float inc = S.inc;
-    int64_t n = -1;
-    float ph = 0.0f;
-    uint32_t w = 0;
-    rec[0].n = -1;
-    rec[0].phase = 0.0f;
-    const int64_t last = (int64_t)S.n_max - 1;
-    while (n < last) {
-        const ClockRun r = clock_asc_run(ph, inc, (uint64_t)(last - n));
-        n += (int64_t)r.steps;
-        if (r.stuck || !(r.x > 1.0f)) break;
-        ph = ssub(r.x, 1.0f); // src/lib.rs:246
-        ++w;
-        if (w >= S.rec_cap) {
-            S.overflow = 1;
-            atomicOr(P.err, DEV_ERR_JIT_OVERFLOW);
-            --w;
-            break;
-        }
-        rec[w].n = (int32_t)n;
-        rec[w].phase = ph;
+    const uint32_t n = jitter_schedule_walk(S.inc, S.n_max, P.jrecs + S.rec_first, S.rec_cap);
+    if (n == 0) {
+        S.overflow = 1;
+        S.n_recs = 1;
+        atomicOr(P.err, DEV_ERR_JIT_OVERFLOW);
+        return;
     }
-    S.n_recs = w + 1;
+    S.n_recs = n;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -250,7 +234,7 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2 (serial form): bit-exact carrier phase and polyBLEP saw, one lane per utterance.  The f32 chain
+// K2 (serial-chain form): bit-exact carrier phase and polyBLEP saw.  The f32 chain
 // phase <- RN(phase + F_t) is the only truly serial dependency of the path; blocks of 8 are run
 // speculatively as bare adds (4 cycles each) and redone carefully only when a wrap falls inside.
 // Output goes straight into the tiled layout k_formant reads with perfectly coalesced 128-bit loads.
@@ -268,62 +252,126 @@ __device__ __forceinline__ float saw_sample(float phase, float f)
     return ssub(ssub(smul(2.0f, phase), 1.0f), polyblep);        // :517
 }
 
-__global__ void __launch_bounds__(32) k_phase_serial(PlanDev P)
+// One warp per utterance.  F_t tiles of 256 samples stream through an 8-deep cp.async ring in shared
+// memory (the prefetch distance hides HBM latency behind ~10k cycles of chain); every lane walks the
+// same chain from broadcast LDS reads, lane 0 parks the phases in shared memory, and at the end of a
+// tile lane l turns block l (8 samples) into saw values and writes one 32-byte sector.
+constexpr int PH_TILE = 256, PH_STAGES = 8, PH_WARPS = 4;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
 {
-    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= P.n_utts) return;
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(PH_WARPS * 32) k_phase_warp(PlanDev P)
+{
+    __shared__ __align__(16) float sF[PH_WARPS][PH_STAGES][PH_TILE];
+    __shared__ __align__(16) float sP[PH_WARPS][PH_TILE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t u = blockIdx.x * PH_WARPS + warp;
+    if (u >= P.n_utts) return;                       // whole warps leave together; only __syncwarp below
     const UttDev& U = P.utts[u];
     const uint32_t n = U.n_samples;
     if (n == 0) return;
-    const float4* src = reinterpret_cast<const float4*>(P.F + U.f_off);
+    const float* src = P.F + U.f_off;
     float* dbg = P.phase_dbg ? P.phase_dbg + U.f_off : nullptr;
     const uint32_t CL = P.chunk_len;
-    float phase = U.init_phase;
-    uint32_t item = U.item_first, j = 0;
-    const uint32_t nblk = (n + 7) >> 3;
-    float4 fa = __ldg(src), fb = __ldg(src + 1);
-    for (uint32_t blk = 0; blk < nblk; ++blk) {
-        float f[8] = { fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w };
-        if (blk + 1 < nblk) { // prefetch the next block while the chain below runs
-            fa = __ldg(src + 2 * (blk + 1));
-            fb = __ldg(src + 2 * (blk + 1) + 1);
-        }
-        const uint32_t valid = min(8u, n - blk * 8);
-        float ph[9];
-        ph[0] = phase;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) ph[k + 1] = sadd(ph[k], f[k]);
-        float fmin8 = f[0];
-#pragma unroll
-        for (int k = 1; k < 8; ++k) fmin8 = fminf(fmin8, f[k]);
-        float s[8];
-        // speculation is valid when no wrap can have happened: increments positive => the chain is
-        // monotone, so its last value bounds all of them (NaNs fail the test and take the slow path)
-        if (valid == 8 && fmin8 > 0.0f && ph[8] < 1.0f) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) s[k] = saw_sample(ph[k], f[k]);
-            if (dbg) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) dbg[blk * 8 + k] = ph[k];
+    const uint32_t npad = (n + 7u) & ~7u;
+    const uint32_t ntiles = (n + PH_TILE - 1) / PH_TILE;
+
+    auto issue = [&](uint32_t tile) {
+        if (tile < ntiles) {
+            const uint32_t off = tile * PH_TILE + lane * 8;
+            float* dst = &sF[warp][tile % PH_STAGES][lane * 8];
+            if (off < npad) {
+                cp_async16(dst, src + off);
+                cp_async16(dst + 4, src + off + 4);
             }
-            phase = ph[8];
-        } else {
+        }
+        cp_async_commit();
+    };
+    for (uint32_t t = 0; t < PH_STAGES - 1; ++t) issue(t);
+
+    float phase = U.init_phase;
+    for (uint32_t tile = 0; tile < ntiles; ++tile) {
+        issue(tile + PH_STAGES - 1);
+        cp_async_wait<PH_STAGES - 1>();
+        __syncwarp();
+        const float* f = sF[warp][tile % PH_STAGES];
+        float* pw = sP[warp];
+        const uint32_t base = tile * PH_TILE;
+        const uint32_t left = n - base;
+        const uint32_t nblk = min(32u, (left + 7u) >> 3);
+        const uint32_t nfull = min(32u, left >> 3);           // blocks with all 8 samples inside the utterance
+        // software pipeline: the next block's increments are already in registers while this block's
+        // chain of 8 dependent adds (the critical path of the whole path) runs
+        float4 na = *reinterpret_cast<const float4*>(f), nb = *reinterpret_cast<const float4*>(f + 4);
+        uint32_t blk = 0;
+        for (; blk < nfull; ++blk) {
+            const float4 fa = na, fb = nb;
+            if (blk + 1 < 32u) {
+                na = *reinterpret_cast<const float4*>(f + blk * 8 + 8);
+                nb = *reinterpret_cast<const float4*>(f + blk * 8 + 12);
+            }
+            const float p0 = phase;
+            const float p1 = sadd(p0, fa.x), p2 = sadd(p1, fa.y), p3 = sadd(p2, fa.z), p4 = sadd(p3, fa.w);
+            const float p5 = sadd(p4, fb.x), p6 = sadd(p5, fb.y), p7 = sadd(p6, fb.z), p8 = sadd(p7, fb.w);
+            // every lane stores the same values to the same address (no divergence on the critical path)
+            *reinterpret_cast<float4*>(pw + blk * 8) = make_float4(p0, p1, p2, p3);
+            *reinterpret_cast<float4*>(pw + blk * 8 + 4) = make_float4(p4, p5, p6, p7);
+            // all increments non-negative (sign bits clear) => the chain is monotone and its last value bounds
+            // the rest, so p8 < 1 proves no wrap happened; a NaN anywhere lands in p8 and fails the comparison
+            const uint32_t signs = __float_as_uint(fa.x) | __float_as_uint(fa.y) | __float_as_uint(fa.z) |
+                                   __float_as_uint(fa.w) | __float_as_uint(fb.x) | __float_as_uint(fb.y) |
+                                   __float_as_uint(fb.z) | __float_as_uint(fb.w);
+            if ((int)signs >= 0 && p8 < 1.0f) {
+                phase = p8;
+            } else { // a wrap (or an odd increment) inside this block: redo it with the reference's test per step
 #pragma unroll 1
-            for (uint32_t k = 0; k < 8; ++k) {
-                s[k] = 0.0f;
-                if (k < valid) {
-                    s[k] = saw_sample(phase, f[k]);
-                    if (dbg) dbg[blk * 8 + k] = phase;
-                    phase = sadd(phase, f[k]);                    // :520
-                    if (phase >= 1.0f) phase = ssub(phase, 1.0f); // :523-525
+                for (uint32_t k = 0; k < 8; ++k) {
+                    pw[blk * 8 + k] = phase;
+                    phase = sadd(phase, f[blk * 8 + k]);              // :520
+                    if (phase >= 1.0f) phase = ssub(phase, 1.0f);     // :523-525
                 }
             }
         }
-        float4* dst = reinterpret_cast<float4*>(P.saw + saw_index(item, j, CL));
-        dst[0] = make_float4(s[0], s[1], s[2], s[3]);
-        dst[1] = make_float4(s[4], s[5], s[6], s[7]);
-        j += 8;
-        if (j >= CL) { j = 0; ++item; }
+        if (blk < nblk) { // ragged tail of the utterance
+            const uint32_t valid = left - blk * 8;
+#pragma unroll 1
+            for (uint32_t k = 0; k < valid; ++k) {
+                pw[blk * 8 + k] = phase;
+                phase = sadd(phase, f[blk * 8 + k]);
+                if (phase >= 1.0f) phase = ssub(phase, 1.0f);
+            }
+        }
+        __syncwarp();
+        if ((uint32_t)lane < nblk) {
+            const float4 fa = *reinterpret_cast<const float4*>(f + lane * 8);
+            const float4 fb = *reinterpret_cast<const float4*>(f + lane * 8 + 4);
+            const float4 pa = *reinterpret_cast<const float4*>(pw + lane * 8);
+            const float4 pb = *reinterpret_cast<const float4*>(pw + lane * 8 + 4);
+            const float fv[8] = { fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w };
+            const float pv[8] = { pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w };
+            const uint32_t b0 = base + lane * 8;
+            const uint32_t valid = min(8u, n - b0);
+            float s[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s[k] = ((uint32_t)k < valid) ? saw_sample(pv[k], fv[k]) : 0.0f;
+            const uint32_t item = U.item_first + b0 / CL, j = b0 % CL;
+            float4* dst = reinterpret_cast<float4*>(P.saw + saw_index(item, j, CL));
+            dst[0] = make_float4(s[0], s[1], s[2], s[3]);
+            dst[1] = make_float4(s[4], s[5], s[6], s[7]);
+            if (dbg) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if ((uint32_t)k < valid) dbg[b0 + k] = pv[k];
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -451,8 +499,10 @@ struct LaneState {
     float a, b, c;
 };
 
+constexpr int FORMANT_WARPS_PER_SM = 32;   // 64 registers per lane
+
 template <int NW>
-__global__ void __launch_bounds__(NW * 32) k_formant(PlanDev P, void* __restrict__ out, int format)
+__global__ void __launch_bounds__(NW * 32, FORMANT_WARPS_PER_SM / NW) k_formant(PlanDev P, void* __restrict__ out, int format)
 {
     __shared__ float part[NW][32][33];
     __shared__ unsigned long long row_out[32];
@@ -585,82 +635,83 @@ __global__ void __launch_bounds__(NW * 32) k_formant(PlanDev P, void* __restrict
             st.ampc = na; st.ampd = lcg_float(st.s_amp) - na;
         }
     };
-    // 8 consecutive samples; v[] receives v1 per sample
-    auto block8 = [&](const float* saw8, float* v) {
-        const bool quiet = (st.time > 9.0f * dt) && (st.jph + 9.0f * jinc < 1.0f);
-        if (quiet) { // no hand-over and no wrap can fall inside: branch-free literal clocks
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                v[k] = sample(saw8[k]);
-                st.time = __fadd_rn(st.time, ndt);
-                st.jph = __fadd_rn(st.jph, jinc);
-            }
-        } else {
-#pragma unroll 1
-            for (int k = 0; k < 8; ++k) {
-                v[k] = sample(saw8[k]);
-                advance_slow();
-            }
-        }
-    };
-
-    // ---- warm-up: [n0 - wmax, n0) in steps of 8, no output
-    for (uint32_t r = wmax; r > 0; r -= 8) {
-        if (on && r <= wmine) {
-            const uint32_t n = it.n0 - r;                 // absolute sample, multiple of 8
-            const uint32_t src_item = U.item_first + n / CL;
-            const float4* sp = reinterpret_cast<const float4*>(P.saw + saw_index(src_item, n % CL, CL));
-            const float4 sa = __ldg(sp), sb = __ldg(sp + 1);
-            const float saw8[8] = { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w };
-            float v[8];
-            block8(saw8, v);
-        }
-    }
-
-    __syncthreads();
+    __syncthreads();   // row_out / row_len visible
     uint32_t lmax = 0;
 #pragma unroll 1
     for (int r = 0; r < 32; ++r) lmax = max(lmax, row_len[r]);
-    const float4* sp = reinterpret_cast<const float4*>(P.saw + saw_index(item_id, 0, CL));
 
-    // ---- main: batches of 32 samples, CTA-wide formant sum + coalesced row stores
-    for (uint32_t base = 0; base < lmax; base += 32) {
-#pragma unroll 1
-        for (int s8 = 0; s8 < 4; ++s8) {
-            const uint32_t r = base + s8 * 8;
-            float v[8];
-            if (on && r < it.len) {
-                const float4 sa = __ldg(sp + (size_t)(r >> 3) * 64), sb = __ldg(sp + (size_t)(r >> 3) * 64 + 1);
-                const float saw8[8] = { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w };
-                block8(saw8, v);
+    // saw source: walks the tiled layout from sample ns; crossing into the next chunk of the utterance (and,
+    // at r == 0, into this lane's own chunk) is a pointer reset every CL samples
+    uint32_t src_item = U.item_first + ns / CL, src_j = ns % CL;
+    const float4* sp = reinterpret_cast<const float4*>(P.saw + saw_index(src_item, src_j, CL));
+
+    // ---- one loop over [-wmax, lmax) in steps of 8: warm-up (r < 0, no output) then the chunk itself
+    for (int r = -(int)wmax; r < (int)lmax; r += 8) {
+        const bool act = on && r >= -(int)wmine && r < (int)it.len;
+        float* dst = &part[w][lane][r & 31];
+        if (act) {
+            const float4 sa = __ldg(sp), sb = __ldg(sp + 1);
+            src_j += 8;
+            if (src_j == CL) {
+                src_j = 0;
+                ++src_item;
+                sp = reinterpret_cast<const float4*>(P.saw + saw_index(src_item, 0, CL));
             } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = 0.0f;
+                sp += 64;
             }
+            const bool quiet = (st.time > 9.0f * dt) && (st.jph + 9.0f * jinc < 1.0f);
+            if (quiet) { // no hand-over and no wrap can fall inside: branch-free literal clocks
+                const float s8[8] = { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w };
+                float v[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) part[w][lane][s8 * 8 + k] = v[k];
-        }
-        __syncthreads();
-        // rows w, w+NW, ...: sum the formants in index order (Array::sum is a left fold, :123) and scale (:574)
-        for (int row = w; row < 32; row += NW) {
-            const uint32_t rl = row_len[row];
-            if (base + lane < rl) {
-                float acc = 0.0f;
+                for (int k = 0; k < 8; ++k) {
+                    v[k] = sample(s8[k]);
+                    st.time = __fadd_rn(st.time, ndt);
+                    st.jph = __fadd_rn(st.jph, jinc);
+                }
+                if (r >= 0) {
 #pragma unroll
-                for (int f = 0; f < NW; ++f) acc += part[f][row][lane];
-                acc *= 0.5f;
-                const unsigned long long o = row_out[row] + base + lane;
-                if (format == GRAIL_F32) {
-                    reinterpret_cast<float*>(out)[o] = acc;
-                } else {
-                    // (x * i16::MAX as f32) as i16: truncating, saturating, NaN -> 0 (examples/cli.rs:50)
-                    const float sc = acc * 32767.0f;
-                    int q = (sc != sc) ? 0 : __float2int_rz(fminf(fmaxf(sc, -32768.0f), 32767.0f));
-                    reinterpret_cast<short*>(out)[o] = (short)q;
+                    for (int k = 0; k < 8; ++k) dst[k] = v[k];
+                }
+            } else {
+#pragma unroll 1
+                for (int k = 0; k < 8; ++k) {
+                    const float4 q = k < 4 ? sa : sb;
+                    const int kk = k & 3;
+                    const float s = kk == 0 ? q.x : (kk == 1 ? q.y : (kk == 2 ? q.z : q.w));
+                    const float v = sample(s);
+                    advance_slow();
+                    if (r >= 0) dst[k] = v;
                 }
             }
+        } else if (r >= 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dst[k] = 0.0f;
         }
-        __syncthreads();
+        if (r >= 0 && (r & 31) == 24) {
+            const uint32_t base = (uint32_t)r - 24u;
+            __syncthreads();
+            // rows w, w+NW, ...: sum the formants in index order (Array::sum is a left fold, :123), scale (:574)
+            for (int row = w; row < 32; row += NW) {
+                const uint32_t rl = row_len[row];
+                if (base + lane < rl) {
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int f = 0; f < NW; ++f) acc += part[f][row][lane];
+                    acc *= 0.5f;
+                    const unsigned long long o = row_out[row] + base + lane;
+                    if (format == GRAIL_F32) {
+                        reinterpret_cast<float*>(out)[o] = acc;
+                    } else {
+                        // (x * i16::MAX as f32) as i16: truncating, saturating, NaN -> 0 (examples/cli.rs:50)
+                        const float sc = acc * 32767.0f;
+                        const int q = (sc != sc) ? 0 : __float2int_rz(fminf(fmaxf(sc, -32768.0f), 32767.0f));
+                        reinterpret_cast<short*>(out)[o] = (short)q;
+                    }
+                }
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -684,10 +735,13 @@ __global__ void __launch_bounds__(256) k_probe_ffma(float* sink, int iters, floa
 
 __global__ void __launch_bounds__(256) k_probe_mufu(float* sink, int iters, float seed)
 {
+    // x <- rcp(x) + 1 (converges to the golden ratio; never folds): one MUFU.RCP + one FADD per step
     float a0 = seed + 1.5f + threadIdx.x, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) { a0 = frcp(a0); a1 = frcp(a1); a2 = frcp(a2); a3 = frcp(a3); }
+        for (int k = 0; k < 16; ++k) {
+            a0 = frcp(a0) + 1.0f; a1 = frcp(a1) + 1.0f; a2 = frcp(a2) + 1.0f; a3 = frcp(a3) + 1.0f;
+        }
     }
     sink[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3;
 }

@@ -129,6 +129,8 @@ struct grail_plan {
     void* d_out = nullptr; size_t d_out_bytes = 0; int d_out_format = -1;
     cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
     bool launched = false;
+    bool jit_on_host = false;   // few distinct jitter increments: schedules computed by the planner
+    std::vector<JitRec> jrecs;
     uint32_t last_launches = 0;
 };
 
@@ -341,6 +343,19 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
     }
     pl->n_jscheds = (uint32_t)pl->jscheds.size();
     pl->n_jrecs = (uint32_t)n_jrecs;
+    // a handful of distinct increments (the common case: one voice) is cheaper on the host than a
+    // latency-bound single-lane kernel; thousands (per-utterance voices) go to k_jitter_schedule
+    if (pl->n_jscheds <= 64) {
+        pl->jit_on_host = true;
+        pl->jrecs.resize(std::max<uint32_t>(pl->n_jrecs, 1));
+        for (auto& js : pl->jscheds) {
+            js.n_recs = jitter_schedule_walk(js.inc, js.n_max, pl->jrecs.data() + js.rec_first, js.rec_cap);
+            if (js.n_recs == 0) {
+                plan_release(pl);
+                return set_err(ctx, GRAIL_ERR_UNSUPPORTED, "jitter schedule overflow");
+            }
+        }
+    }
 
     // ---- chunking: aim for one resident wave of k_formant CTAs (32 chunks each)
     uint64_t target = ctx->target_items;
@@ -349,11 +364,23 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
         if (occ < 1) occ = 1;
         target = (uint64_t)ctx->prop.multiProcessorCount * (uint64_t)occ * 32ull;
     }
-    uint64_t cl = (total + target - 1) / std::max<uint64_t>(target, 1);
-    cl = std::max<uint64_t>(cl, ctx->min_chunk);
-    cl = std::min<uint64_t>(cl, ctx->max_chunk);
-    cl = std::min<uint64_t>(cl, std::max<uint32_t>(n_max, 32u));
-    cl = (cl + 31) & ~31ull;
+    // smallest chunk length (multiple of 32) whose work items still fit in `target` lanes: the grid is then a
+    // single full wave with no tail; when even one chunk per utterance does not fit, utterances stay whole
+    auto items_at = [&](uint64_t c) {
+        uint64_t n = 0;
+        for (uint32_t u = 0; u < n_utts; ++u) n += (pl->utts[u].n_samples + c - 1) / c;
+        return n;
+    };
+    const uint64_t cl_hi = ((uint64_t)std::max<uint32_t>(n_max, 32u) + 31) & ~31ull;
+    uint64_t lo = 1, hi = cl_hi / 32;   // in units of 32 samples
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) / 2;
+        if (items_at(mid * 32) <= target) hi = mid; else lo = mid + 1;
+    }
+    uint64_t cl = lo * 32;
+    cl = std::max<uint64_t>(cl, (ctx->min_chunk + 31) & ~31u);
+    cl = std::min<uint64_t>(cl, std::max<uint64_t>((ctx->max_chunk + 31) & ~31u, 32));
+    cl = std::min<uint64_t>(cl, cl_hi);
     pl->chunk_len = (uint32_t)cl;
 
     // ---- work items: utterances in descending length so a CTA's 32 chunks are of similar size
@@ -407,6 +434,7 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
     if (n_utts) CUF(cudaMemcpyAsync(pl->d_utts, pl->utts.data(), n_utts * sizeof(UttDev), cudaMemcpyHostToDevice, s));
     if (pl->n_items) CUF(cudaMemcpyAsync(pl->d_items, pl->items.data(), pl->n_items * sizeof(ItemDev), cudaMemcpyHostToDevice, s));
     if (pl->n_jscheds) CUF(cudaMemcpyAsync(pl->d_jscheds, pl->jscheds.data(), pl->n_jscheds * sizeof(JitSchedDev), cudaMemcpyHostToDevice, s));
+    if (pl->jit_on_host && pl->n_jrecs) CUF(cudaMemcpyAsync(pl->d_jrecs, pl->jrecs.data(), (size_t)pl->n_jrecs * sizeof(JitRec), cudaMemcpyHostToDevice, s));
     for (auto& e : pl->ev) CUF(cudaEventCreate(&e));
     // the host vectors are read by the async copies above: make them safe to outlive this call
     CUF(cudaStreamSynchronize(s));
@@ -426,7 +454,7 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
     pl->last_launches = 0;
     CU(ctx, cudaMemsetAsync(pl->d_err, 0, 4, s));
     CU(ctx, cudaEventRecord(pl->ev[0], s));
-    if (pl->n_items) {
+    if (pl->n_items && !pl->jit_on_host) {
         k_jitter_schedule<<<(pl->n_jscheds + 63) / 64, 64, 0, s>>>(P);
         pl->last_launches++;
     }
@@ -439,7 +467,7 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
     }
     CU(ctx, cudaEventRecord(pl->ev[2], s));
     if (pl->n_items) {
-        k_phase_serial<<<(pl->n_utts + 31) / 32, 32, 0, s>>>(P);
+        k_phase_warp<<<(pl->n_utts + PH_WARPS - 1) / PH_WARPS, PH_WARPS * 32, 0, s>>>(P);
         pl->last_launches++;
     }
     CU(ctx, cudaEventRecord(pl->ev[3], s));

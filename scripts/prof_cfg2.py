@@ -1,0 +1,15 @@
+"""profiling driver: config 2 (optionally smaller) resident plan, a few launches (used under ncu)"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import grail_rs_b200 as g
+from grail_rs_b200 import workloads as W
+n_utts = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+ctx = g.Context(0)
+elems, offs, vp = W.config2(n_utts, 10)
+plan = ctx.plan(elems, offs, vp)
+d = plan.device_output()
+for i in range(reps):
+    plan.launch(d)
+    ctx.synchronize()
+    print(plan.timings())
