@@ -2,7 +2,7 @@
 //
 //   k_jitter_schedule  exact wrap schedule of the value-noise phase clock      (src/lib.rs:242-251)
 //   k_frequency        bit-exact per-sample fundamental F_t                     (src/lib.rs:861-931, 753-763)
-//   k_phase_warp       bit-exact carrier phase + polyBLEP saw, one warp/utt     (src/lib.rs:503-525)
+//   k_phase_pair       bit-exact carrier phase + polyBLEP saw, two warps/utt    (src/lib.rs:503-525)
 //   k_formant<NW>      noise, low-pass, turbulence, SVF band-pass, formant sum  (src/lib.rs:528-577, 764-773)
 //
 // Exactness classes: the clocks, the LCG streams, F_t, the carrier phase and the saw are
@@ -239,7 +239,50 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
 // speculatively as bare adds (4 cycles each) and redone carefully only when a wrap falls inside.
 // Output goes straight into the tiled layout k_formant reads with perfectly coalesced 128-bit loads.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float saw_sample(float phase, float f)
+// CTA = 4 utterances x 2 warps.  Warps 0-3 each own one utterance's chain (one per SM sub-partition):
+// F_t tiles of 256 samples stream through an 8-deep cp.async ring in shared memory (the prefetch distance
+// hides HBM latency), every lane walks the same chain from broadcast LDS reads and lane 0 parks the phases in
+// a double-buffered shared tile.  Warps 4-7 turn each finished tile into polyBLEP saw values (lane l takes
+// 8 samples = one 32-byte sector) while the chain warp is already on the next tile; producer and consumer
+// meet on mbarriers (full / empty per buffer).
+constexpr int PH_TILE = 256, PH_STAGES = 8, PH_AHEAD = 6, PH_UTTS = 4;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{ .reg .b64 t; mbarrier.arrive.shared::cta.b64 t, [%0]; }" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(a), "r"(parity)
+        : "memory");
+}
+
+// the rare edge samples of the saw (one before and one after each carrier wrap), kept out of line
+__device__ __noinline__ float saw_edge(float phase, float f)
 {
     float polyblep = 0.0f;
     if (phase < f) {                                             // :503-506
@@ -252,126 +295,165 @@ __device__ __forceinline__ float saw_sample(float phase, float f)
     return ssub(ssub(smul(2.0f, phase), 1.0f), polyblep);        // :517
 }
 
-// One warp per utterance.  F_t tiles of 256 samples stream through an 8-deep cp.async ring in shared
-// memory (the prefetch distance hides HBM latency behind ~10k cycles of chain); every lane walks the
-// same chain from broadcast LDS reads, lane 0 parks the phases in shared memory, and at the end of a
-// tile lane l turns block l (8 samples) into saw values and writes one 32-byte sector.
-constexpr int PH_TILE = 256, PH_STAGES = 8, PH_WARPS = 4;
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+__global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
 {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__global__ void __launch_bounds__(PH_WARPS * 32) k_phase_warp(PlanDev P)
-{
-    __shared__ __align__(16) float sF[PH_WARPS][PH_STAGES][PH_TILE];
-    __shared__ __align__(16) float sP[PH_WARPS][PH_TILE];
+    __shared__ __align__(16) float sF[PH_UTTS][PH_STAGES][PH_TILE];
+    __shared__ __align__(16) float sP[PH_UTTS][2][PH_TILE];
+    __shared__ __align__(8) uint64_t s_full[PH_UTTS][2], s_empty[PH_UTTS][2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t u = blockIdx.x * PH_WARPS + warp;
-    if (u >= P.n_utts) return;                       // whole warps leave together; only __syncwarp below
+    const int slot = warp & (PH_UTTS - 1);
+    const bool is_chain = warp < PH_UTTS;
+    if (threadIdx.x < PH_UTTS * 2) {
+        mbar_init(&s_full[threadIdx.x >> 1][threadIdx.x & 1], 1);
+        mbar_init(&s_empty[threadIdx.x >> 1][threadIdx.x & 1], 1);
+    }
+    __syncthreads();
+    const uint32_t u = blockIdx.x * PH_UTTS + slot;
+    if (u >= P.n_utts) return;
     const UttDev& U = P.utts[u];
     const uint32_t n = U.n_samples;
     if (n == 0) return;
-    const float* src = P.F + U.f_off;
-    float* dbg = P.phase_dbg ? P.phase_dbg + U.f_off : nullptr;
-    const uint32_t CL = P.chunk_len;
-    const uint32_t npad = (n + 7u) & ~7u;
     const uint32_t ntiles = (n + PH_TILE - 1) / PH_TILE;
 
-    auto issue = [&](uint32_t tile) {
-        if (tile < ntiles) {
-            const uint32_t off = tile * PH_TILE + lane * 8;
-            float* dst = &sF[warp][tile % PH_STAGES][lane * 8];
-            if (off < npad) {
-                cp_async16(dst, src + off);
-                cp_async16(dst + 4, src + off + 4);
+    if (is_chain) {
+        // ---------------- chain warp ----------------
+        const float* src = P.F + U.f_off;
+        const uint32_t npad = (n + 7u) & ~7u;
+        auto issue = [&](uint32_t tile) {
+            if (tile < ntiles) {
+                const uint32_t off = tile * PH_TILE + lane * 8;
+                float* dst = &sF[slot][tile % PH_STAGES][lane * 8];
+                if (off < npad) {
+                    cp_async16(dst, src + off);
+                    cp_async16(dst + 4, src + off + 4);
+                }
             }
-        }
-        cp_async_commit();
-    };
-    for (uint32_t t = 0; t < PH_STAGES - 1; ++t) issue(t);
-
-    float phase = U.init_phase;
-    for (uint32_t tile = 0; tile < ntiles; ++tile) {
-        issue(tile + PH_STAGES - 1);
-        cp_async_wait<PH_STAGES - 1>();
-        __syncwarp();
-        const float* f = sF[warp][tile % PH_STAGES];
-        float* pw = sP[warp];
-        const uint32_t base = tile * PH_TILE;
-        const uint32_t left = n - base;
-        const uint32_t nblk = min(32u, (left + 7u) >> 3);
-        const uint32_t nfull = min(32u, left >> 3);           // blocks with all 8 samples inside the utterance
-        // software pipeline: the next block's increments are already in registers while this block's
-        // chain of 8 dependent adds (the critical path of the whole path) runs
-        float4 na = *reinterpret_cast<const float4*>(f), nb = *reinterpret_cast<const float4*>(f + 4);
-        uint32_t blk = 0;
-        for (; blk < nfull; ++blk) {
-            const float4 fa = na, fb = nb;
-            if (blk + 1 < 32u) {
-                na = *reinterpret_cast<const float4*>(f + blk * 8 + 8);
-                nb = *reinterpret_cast<const float4*>(f + blk * 8 + 12);
-            }
-            const float p0 = phase;
-            const float p1 = sadd(p0, fa.x), p2 = sadd(p1, fa.y), p3 = sadd(p2, fa.z), p4 = sadd(p3, fa.w);
-            const float p5 = sadd(p4, fb.x), p6 = sadd(p5, fb.y), p7 = sadd(p6, fb.z), p8 = sadd(p7, fb.w);
-            // every lane stores the same values to the same address (no divergence on the critical path)
-            *reinterpret_cast<float4*>(pw + blk * 8) = make_float4(p0, p1, p2, p3);
-            *reinterpret_cast<float4*>(pw + blk * 8 + 4) = make_float4(p4, p5, p6, p7);
-            // all increments non-negative (sign bits clear) => the chain is monotone and its last value bounds
-            // the rest, so p8 < 1 proves no wrap happened; a NaN anywhere lands in p8 and fails the comparison
-            const uint32_t signs = __float_as_uint(fa.x) | __float_as_uint(fa.y) | __float_as_uint(fa.z) |
-                                   __float_as_uint(fa.w) | __float_as_uint(fb.x) | __float_as_uint(fb.y) |
-                                   __float_as_uint(fb.z) | __float_as_uint(fb.w);
-            if ((int)signs >= 0 && p8 < 1.0f) {
-                phase = p8;
-            } else { // a wrap (or an odd increment) inside this block: redo it with the reference's test per step
+            cp_async_commit();
+        };
+        for (uint32_t t = 0; t < PH_AHEAD; ++t) issue(t);
+        float phase = U.init_phase;
+        const bool lane0 = lane == 0;
+        for (uint32_t tile = 0; tile < ntiles; ++tile) {
+            const int buf = tile & 1;
+            issue(tile + PH_AHEAD);             // stage (tile-2) % 8: released by the saw warp two tiles ago
+            cp_async_wait<PH_AHEAD>();
+            __syncwarp();
+            mbar_wait(&s_empty[slot][buf], ((tile >> 1) & 1) ^ 1);   // first use of each buffer passes at once
+            const float* f = sF[slot][tile % PH_STAGES];
+            float* pw = sP[slot][buf];
+            const uint32_t left = n - tile * PH_TILE;
+            const uint32_t nblk = min(32u, (left + 7u) >> 3);
+            const uint32_t nfull = min(32u, left >> 3);   // blocks with all 8 samples inside the utterance
+            // 8 samples from shared memory, speculating "no wrap"; falls back to the reference's per-step test
+            auto block8 = [&](uint32_t blk) {
+                const float4 fa = *reinterpret_cast<const float4*>(f + blk * 8);
+                const float4 fb = *reinterpret_cast<const float4*>(f + blk * 8 + 4);
+                const float p0 = phase;
+                const float p1 = sadd(p0, fa.x), p2 = sadd(p1, fa.y), p3 = sadd(p2, fa.z), p4 = sadd(p3, fa.w);
+                const float p5 = sadd(p4, fb.x), p6 = sadd(p5, fb.y), p7 = sadd(p6, fb.z), p8 = sadd(p7, fb.w);
+                const uint32_t signs = __float_as_uint(fa.x) | __float_as_uint(fa.y) | __float_as_uint(fa.z) |
+                                       __float_as_uint(fa.w) | __float_as_uint(fb.x) | __float_as_uint(fb.y) |
+                                       __float_as_uint(fb.z) | __float_as_uint(fb.w);
+                if ((int)signs >= 0 && p8 < 1.0f) {
+                    if (lane0) {
+                        *reinterpret_cast<float4*>(pw + blk * 8) = make_float4(p0, p1, p2, p3);
+                        *reinterpret_cast<float4*>(pw + blk * 8 + 4) = make_float4(p4, p5, p6, p7);
+                    }
+                    phase = p8;
+                } else {
 #pragma unroll 1
-                for (uint32_t k = 0; k < 8; ++k) {
-                    pw[blk * 8 + k] = phase;
-                    phase = sadd(phase, f[blk * 8 + k]);              // :520
-                    if (phase >= 1.0f) phase = ssub(phase, 1.0f);     // :523-525
+                    for (uint32_t k = 0; k < 8; ++k) {
+                        if (lane0) pw[blk * 8 + k] = phase;
+                        phase = sadd(phase, f[blk * 8 + k]);              // :520
+                        if (phase >= 1.0f) phase = ssub(phase, 1.0f);     // :523-525
+                    }
+                }
+            };
+            // main loop: 32 samples per iteration as ONE basic block: a chain of 32 dependent adds (the critical
+            // path of the whole path, 4 cycles each) with the loads, the sign test and lane 0's speculative phase
+            // stores issued in its shadow.  All increments non-negative (sign bits clear) => the chain is monotone
+            // and its last value bounds the rest, so p32 < 1 proves no wrap happened; a NaN anywhere lands in the
+            // last value and fails the test.  On failure the 32 samples are redone (the stores are overwritten).
+            const uint32_t nquad = nfull >> 2;
+            for (uint32_t q = 0; q < nquad; ++q) {
+                float4 fv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) fv[i] = *reinterpret_cast<const float4*>(f + q * 32 + i * 4);
+                float p = phase;
+                uint32_t signs = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float a0 = p;
+                    const float a1 = sadd(a0, fv[i].x), a2 = sadd(a1, fv[i].y), a3 = sadd(a2, fv[i].z);
+                    p = sadd(a3, fv[i].w);
+                    if (lane0) *reinterpret_cast<float4*>(pw + q * 32 + i * 4) = make_float4(a0, a1, a2, a3);
+                    signs |= __float_as_uint(fv[i].x) | __float_as_uint(fv[i].y) | __float_as_uint(fv[i].z) |
+                             __float_as_uint(fv[i].w);
+                }
+                if ((int)signs >= 0 && p < 1.0f) {
+                    phase = p;
+                } else { // a carrier wrap inside these 32 samples: redo them 8 at a time
+#pragma unroll 1
+                    for (uint32_t b = 0; b < 4; ++b) block8(q * 4 + b);
+                }
+            }
+            uint32_t blk = nquad * 4;
+#pragma unroll 1
+            for (; blk < nfull; ++blk) block8(blk);
+            if (blk < nblk) { // ragged tail of the utterance
+                const uint32_t valid = left - blk * 8;
+#pragma unroll 1
+                for (uint32_t k = 0; k < valid; ++k) {
+                    if (lane0) pw[blk * 8 + k] = phase;
+                    phase = sadd(phase, f[blk * 8 + k]);
+                    if (phase >= 1.0f) phase = ssub(phase, 1.0f);
+                }
+            }
+            __syncwarp();
+            if (lane0) mbar_arrive(&s_full[slot][buf]);   // release: the tile's phases (and its F stage) are ready
+        }
+    } else {
+        // ---------------- saw warp ----------------
+        float* dbg = P.phase_dbg ? P.phase_dbg + U.f_off : nullptr;
+        const uint32_t CL = P.chunk_len;
+        for (uint32_t tile = 0; tile < ntiles; ++tile) {
+            const int buf = tile & 1;
+            mbar_wait(&s_full[slot][buf], (tile >> 1) & 1);
+            const float* f = sF[slot][tile % PH_STAGES];
+            const float* pw = sP[slot][buf];
+            const uint32_t b0 = tile * PH_TILE + lane * 8;
+            float4 fa, fb, pa, pb;
+            if (b0 < n) {
+                fa = *reinterpret_cast<const float4*>(f + lane * 8);
+                fb = *reinterpret_cast<const float4*>(f + lane * 8 + 4);
+                pa = *reinterpret_cast<const float4*>(pw + lane * 8);
+                pb = *reinterpret_cast<const float4*>(pw + lane * 8 + 4);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[slot][buf]);   // both shared tiles are in registers now
+            if (b0 < n) {
+                const float fv[8] = { fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w };
+                const float pv[8] = { pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w };
+                const uint32_t valid = min(8u, n - b0);
+                float s[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    s[k] = ssub(smul(2.0f, pv[k]), 1.0f);                               // :517 with polyblep = 0
+                    const bool edge = !((pv[k] >= fv[k]) && (pv[k] <= ssub(1.0f, fv[k])));
+                    if (edge) s[k] = saw_edge(pv[k], fv[k]);
+                    if ((uint32_t)k >= valid) s[k] = 0.0f;
+                }
+                const uint32_t item = U.item_first + b0 / CL, j = b0 % CL;
+                float4* dst = reinterpret_cast<float4*>(P.saw + saw_index(item, j, CL));
+                dst[0] = make_float4(s[0], s[1], s[2], s[3]);
+                dst[1] = make_float4(s[4], s[5], s[6], s[7]);
+                if (dbg) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if ((uint32_t)k < valid) dbg[b0 + k] = pv[k];
                 }
             }
         }
-        if (blk < nblk) { // ragged tail of the utterance
-            const uint32_t valid = left - blk * 8;
-#pragma unroll 1
-            for (uint32_t k = 0; k < valid; ++k) {
-                pw[blk * 8 + k] = phase;
-                phase = sadd(phase, f[blk * 8 + k]);
-                if (phase >= 1.0f) phase = ssub(phase, 1.0f);
-            }
-        }
-        __syncwarp();
-        if ((uint32_t)lane < nblk) {
-            const float4 fa = *reinterpret_cast<const float4*>(f + lane * 8);
-            const float4 fb = *reinterpret_cast<const float4*>(f + lane * 8 + 4);
-            const float4 pa = *reinterpret_cast<const float4*>(pw + lane * 8);
-            const float4 pb = *reinterpret_cast<const float4*>(pw + lane * 8 + 4);
-            const float fv[8] = { fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w };
-            const float pv[8] = { pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w };
-            const uint32_t b0 = base + lane * 8;
-            const uint32_t valid = min(8u, n - b0);
-            float s[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) s[k] = ((uint32_t)k < valid) ? saw_sample(pv[k], fv[k]) : 0.0f;
-            const uint32_t item = U.item_first + b0 / CL, j = b0 % CL;
-            float4* dst = reinterpret_cast<float4*>(P.saw + saw_index(item, j, CL));
-            dst[0] = make_float4(s[0], s[1], s[2], s[3]);
-            dst[1] = make_float4(s[4], s[5], s[6], s[7]);
-            if (dbg) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if ((uint32_t)k < valid) dbg[b0 + k] = pv[k];
-            }
-        }
-        __syncwarp();
     }
 }
 
@@ -645,20 +727,31 @@ __global__ void __launch_bounds__(NW * 32, FORMANT_WARPS_PER_SM / NW) k_formant(
     uint32_t src_item = U.item_first + ns / CL, src_j = ns % CL;
     const float4* sp = reinterpret_cast<const float4*>(P.saw + saw_index(src_item, src_j, CL));
 
+    // saw values are fetched one iteration ahead (register double buffer) so the L2 latency of the
+    // coalesced 128-bit loads is covered by a whole block of arithmetic
+    float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
+    auto fetch = [&]() {
+        na = __ldg(sp);
+        nb = __ldg(sp + 1);
+        src_j += 8;
+        if (src_j == CL) {
+            src_j = 0;
+            ++src_item;
+            sp = reinterpret_cast<const float4*>(P.saw + saw_index(src_item, 0, CL));
+        } else {
+            sp += 64;
+        }
+    };
+    auto active_at = [&](int r) { return on && r >= -(int)wmine && r < (int)it.len; };
+    if (active_at(-(int)wmax)) fetch();
+
     // ---- one loop over [-wmax, lmax) in steps of 8: warm-up (r < 0, no output) then the chunk itself
     for (int r = -(int)wmax; r < (int)lmax; r += 8) {
-        const bool act = on && r >= -(int)wmine && r < (int)it.len;
+        const bool act = active_at(r);
         float* dst = &part[w][lane][r & 31];
+        const float4 sa = na, sb = nb;
+        if (active_at(r + 8)) fetch();
         if (act) {
-            const float4 sa = __ldg(sp), sb = __ldg(sp + 1);
-            src_j += 8;
-            if (src_j == CL) {
-                src_j = 0;
-                ++src_item;
-                sp = reinterpret_cast<const float4*>(P.saw + saw_index(src_item, 0, CL));
-            } else {
-                sp += 64;
-            }
             const bool quiet = (st.time > 9.0f * dt) && (st.jph + 9.0f * jinc < 1.0f);
             if (quiet) { // no hand-over and no wrap can fall inside: branch-free literal clocks
                 const float s8[8] = { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w };

@@ -35,7 +35,7 @@ struct grail_ctx {
     std::string    err;
     std::vector<PoolBuf> pool;
     // options
-    double   warmup_nepers = 16.1;
+    double   warmup_nepers = 13.8;   // exp(-13.8) = 1e-6: measured below the f32 noise floor of the path
     uint32_t target_items = 0;      // 0 = one resident wave of k_formant CTAs
     uint32_t min_chunk = 2048;
     uint32_t max_chunk = 1u << 22;
@@ -467,7 +467,7 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
     }
     CU(ctx, cudaEventRecord(pl->ev[2], s));
     if (pl->n_items) {
-        k_phase_warp<<<(pl->n_utts + PH_WARPS - 1) / PH_WARPS, PH_WARPS * 32, 0, s>>>(P);
+        k_phase_pair<<<(pl->n_utts + PH_UTTS - 1) / PH_UTTS, PH_UTTS * 64, 0, s>>>(P);
         pl->last_launches++;
     }
     CU(ctx, cudaEventRecord(pl->ev[3], s));

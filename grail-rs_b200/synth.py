@@ -161,9 +161,13 @@ class Context:
             raise GrailError(rc)
         self._h = h
         self.device = device
+        self._pinned = []
 
     def close(self):
         if getattr(self, "_h", None):
+            for p in self._pinned:
+                self._L.grail_cuda_host_free(self._h, p)
+            self._pinned = []
             self._L.grail_cuda_destroy(self._h)
             self._h = None
 
@@ -195,9 +199,8 @@ class Context:
         p = C.c_void_p()
         self._check(self._L.grail_cuda_host_alloc(self._h, max(nbytes, 1), C.byref(p)))
         buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
-        arr = np.frombuffer(buf, dtype=dtype, count=int(n))
-        arr._grail_pinned = p  # keep the address alive with the array object
-        return arr
+        self._pinned.append(p)      # owned by the context; released in close()
+        return np.frombuffer(buf, dtype=dtype, count=int(n))
 
     def probe_fp32_peak(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()

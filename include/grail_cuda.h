@@ -104,7 +104,7 @@ const char* grail_cuda_last_error(const grail_ctx* ctx);
 /* the ctx's cudaStream_t as an opaque pointer (for event timing / interop) */
 void* grail_cuda_stream_handle(grail_ctx* ctx);
 int  grail_cuda_synchronize(grail_ctx* ctx);
-/* tuning knobs: "warmup_nepers" (float, filter warm-up depth, default 16.1 ~ 1e-7),
+/* tuning knobs: "warmup_nepers" (float, filter warm-up depth, default 13.8 ~ 1e-6),
  * "target_lanes" (int, time-chunks the planner aims for), "max_chunk" / "min_chunk" (samples) */
 int  grail_cuda_set_option(grail_ctx* ctx, const char* key, double value);
 
