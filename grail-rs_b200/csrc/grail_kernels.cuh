@@ -64,9 +64,10 @@ struct PlanDev {
     float*              F;         // linear, per utterance at f_off
     float*              saw;       // tiled: [group][j/8][lane][8]
     float*              phase_dbg; // optional linear carrier phase tap (same indexing as F), may be null
+    uint32_t*           fflags;    // one word per 128 F_t entries: nonzero if any is negative or NaN
     uint32_t*           err;       // device error word
     uint32_t n_utts, n_items, n_groups, n_jscheds;
-    uint32_t chunk_len;            // CL, multiple of 32
+    uint32_t chunk_len;            // CL, multiple of 256
     float    warmup_nepers;
 };
 
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
     float nxt = lcg_float(s_next);
 
     float* dst = P.F + U.f_off + ns;
+    bool odd = false;   // any increment that is negative or NaN: k_phase then takes its fully general path
     // one sample of the scalar frequency path, strict ops in the reference's order
     auto freq_sample = [&]() -> float {
         float fb;
@@ -193,7 +195,9 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
             fb = sadd(smul(seg.xf, ssub(1.0f, alpha)), smul(seg.yf, alpha));               // :406
         }
         const float n0 = sadd(smul(cur, ssub(1.0f, jph)), smul(nxt, jph));                 // :254
-        return sadd(fb, smul(n0, dfreq));                                                  // :763
+        const float fr = sadd(fb, smul(n0, dfreq));                                        // :763
+        odd |= !(fr >= 0.0f);
+        return fr;
     };
     for (uint32_t k0 = 0; k0 < count; k0 += 8) {
         const bool quiet = (k0 + 8 <= count) && (time > 9.0f * dt) && (jph + 9.0f * jinc < 1.0f);
@@ -231,6 +235,7 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
             }
         }
     }
+    P.fflags[(U.f_off + ns) >> 7] = odd ? 1u : 0u;   // runs are 128-aligned (CL and f_off are multiples of 256)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -241,10 +246,12 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
 // ------------------------------------------------------------------------------------------------
 // CTA = 4 utterances x 2 warps.  Warps 0-3 each own one utterance's chain (one per SM sub-partition):
 // F_t tiles of 256 samples stream through an 8-deep cp.async ring in shared memory (the prefetch distance
-// hides HBM latency), every lane walks the same chain from broadcast LDS reads and lane 0 parks the phases in
-// a double-buffered shared tile.  Warps 4-7 turn each finished tile into polyBLEP saw values (lane l takes
-// 8 samples = one 32-byte sector) while the chain warp is already on the next tile; producer and consumer
-// meet on mbarriers (full / empty per buffer).
+// hides HBM latency), every lane walks the same chain from broadcast LDS reads and lane 0 parks the phase at
+// the start of every 8-sample block in a double-buffered shared tile -- nothing else is on the chain warp's
+// instruction stream, because a lone warp issues only about one instruction every four cycles.  Warps 4-7
+// take each finished tile: lane l replays block l's 8 steps from its start phase (exactly, with the
+// reference's wrap test), forms the polyBLEP saw and writes one 32-byte sector, while the chain warp is
+// already on the next tile.  Producer and consumer meet on mbarriers (full / empty per buffer).
 constexpr int PH_TILE = 256, PH_STAGES = 8, PH_AHEAD = 6, PH_UTTS = 4;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
@@ -281,6 +288,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
         : "memory");
 }
 
+// explicit shared-window accesses (32-bit addresses): keeps generic-address arithmetic out of the chain loop
+__device__ __forceinline__ float4 lds128(unsigned a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(unsigned a, float x, float y, float z, float w)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void sts32(unsigned a, float x) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory"); }
+__device__ __forceinline__ unsigned lds32u(unsigned a)
+{
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void cp_async8(unsigned sa, const void* gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+
 // the rare edge samples of the saw (one before and one after each carrier wrap), kept out of line
 __device__ __noinline__ float saw_edge(float phase, float f)
 {
@@ -295,11 +325,42 @@ __device__ __noinline__ float saw_edge(float phase, float f)
     return ssub(ssub(smul(2.0f, phase), 1.0f), polyblep);        // :517
 }
 
+// 8 steps exactly as the reference takes them (any increment, any wrap)  :520-525
+__device__ __forceinline__ float phase_steps8(float phase, const float4& fa, const float4& fb, uint32_t valid)
+{
+    const float fv[8] = { fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w };
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if ((uint32_t)k < valid) {
+            phase = sadd(phase, fv[k]);
+            if (phase >= 1.0f) phase = ssub(phase, 1.0f);
+        }
+    }
+    return phase;
+}
+
+// one 32-sample quad that contains a carrier wrap, redone 8 samples at a time (rare: kept out of line so the
+// chain warp's straight-line code stays small); f_a / p_a are shared-window addresses of the quad's F_t and
+// of its four block-start phase slots
+__device__ __noinline__ float phase_redo_quad(float phase, unsigned f_a, unsigned p_a, bool lane0)
+{
+#pragma unroll 1
+    for (uint32_t b = 0; b < 4; ++b) {
+        const float4 fa = lds128(f_a + b * 32), fb = lds128(f_a + b * 32 + 16);
+        if (lane0) sts32(p_a + b * 4, phase);
+        const float p4 = sadd(sadd(sadd(sadd(phase, fa.x), fa.y), fa.z), fa.w);
+        const float p8 = sadd(sadd(sadd(sadd(p4, fb.x), fb.y), fb.z), fb.w);
+        phase = (p8 < 1.0f) ? p8 : phase_steps8(phase, fa, fb, 8);
+    }
+    return phase;
+}
+
 __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
 {
     __shared__ __align__(16) float sF[PH_UTTS][PH_STAGES][PH_TILE];
-    __shared__ __align__(16) float sP[PH_UTTS][2][PH_TILE];
+    __shared__ __align__(16) float sP[PH_UTTS][2][32];          // phase at the start of each 8-sample block
     __shared__ __align__(8) uint64_t s_full[PH_UTTS][2], s_empty[PH_UTTS][2];
+    __shared__ __align__(8) uint32_t sFlag[PH_UTTS][PH_STAGES][2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = warp & (PH_UTTS - 1);
     const bool is_chain = warp < PH_UTTS;
@@ -318,7 +379,11 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
     if (is_chain) {
         // ---------------- chain warp ----------------
         const float* src = P.F + U.f_off;
+        const uint32_t* flags = P.fflags + (U.f_off >> 7);   // f_off is a multiple of 256: 8-byte aligned pairs
         const uint32_t npad = (n + 7u) & ~7u;
+        const unsigned sF_a = (unsigned)__cvta_generic_to_shared(&sF[slot][0][0]);
+        const unsigned sP_a = (unsigned)__cvta_generic_to_shared(&sP[slot][0][0]);
+        const unsigned sG_a = (unsigned)__cvta_generic_to_shared(&sFlag[slot][0][0]);
         auto issue = [&](uint32_t tile) {
             if (tile < ntiles) {
                 const uint32_t off = tile * PH_TILE + lane * 8;
@@ -327,6 +392,8 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
                     cp_async16(dst, src + off);
                     cp_async16(dst + 4, src + off + 4);
                 }
+                // the tile's two sign-flag words ride the same ring (the flag array is padded past the end)
+                if (lane == 0) cp_async8(sG_a + (tile % PH_STAGES) * 8, flags + 2 * tile);
             }
             cp_async_commit();
         };
@@ -339,74 +406,40 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
             cp_async_wait<PH_AHEAD>();
             __syncwarp();
             mbar_wait(&s_empty[slot][buf], ((tile >> 1) & 1) ^ 1);   // first use of each buffer passes at once
-            const float* f = sF[slot][tile % PH_STAGES];
-            float* pw = sP[slot][buf];
+            const unsigned fa_ = sF_a + (tile % PH_STAGES) * (PH_TILE * 4);   // this tile's F_t
+            const unsigned pa_ = sP_a + buf * (32 * 4);                        // block-start phases out
+            const uint32_t odd = lds32u(sG_a + (tile % PH_STAGES) * 8) | lds32u(sG_a + (tile % PH_STAGES) * 8 + 4);
             const uint32_t left = n - tile * PH_TILE;
             const uint32_t nblk = min(32u, (left + 7u) >> 3);
-            const uint32_t nfull = min(32u, left >> 3);   // blocks with all 8 samples inside the utterance
-            // 8 samples from shared memory, speculating "no wrap"; falls back to the reference's per-step test
-            auto block8 = [&](uint32_t blk) {
-                const float4 fa = *reinterpret_cast<const float4*>(f + blk * 8);
-                const float4 fb = *reinterpret_cast<const float4*>(f + blk * 8 + 4);
-                const float p0 = phase;
-                const float p1 = sadd(p0, fa.x), p2 = sadd(p1, fa.y), p3 = sadd(p2, fa.z), p4 = sadd(p3, fa.w);
-                const float p5 = sadd(p4, fb.x), p6 = sadd(p5, fb.y), p7 = sadd(p6, fb.z), p8 = sadd(p7, fb.w);
-                const uint32_t signs = __float_as_uint(fa.x) | __float_as_uint(fa.y) | __float_as_uint(fa.z) |
-                                       __float_as_uint(fa.w) | __float_as_uint(fb.x) | __float_as_uint(fb.y) |
-                                       __float_as_uint(fb.z) | __float_as_uint(fb.w);
-                if ((int)signs >= 0 && p8 < 1.0f) {
-                    if (lane0) {
-                        *reinterpret_cast<float4*>(pw + blk * 8) = make_float4(p0, p1, p2, p3);
-                        *reinterpret_cast<float4*>(pw + blk * 8 + 4) = make_float4(p4, p5, p6, p7);
-                    }
-                    phase = p8;
-                } else {
+            if (odd || left < PH_TILE) {
+                // a tile with a negative / NaN increment somewhere, or the ragged last tile: fully general path
 #pragma unroll 1
-                    for (uint32_t k = 0; k < 8; ++k) {
-                        if (lane0) pw[blk * 8 + k] = phase;
-                        phase = sadd(phase, f[blk * 8 + k]);              // :520
-                        if (phase >= 1.0f) phase = ssub(phase, 1.0f);     // :523-525
-                    }
+                for (uint32_t blk = 0; blk < nblk; ++blk) {
+                    const float4 fa = lds128(fa_ + blk * 32), fb = lds128(fa_ + blk * 32 + 16);
+                    if (lane0) sts32(pa_ + blk * 4, phase);
+                    phase = phase_steps8(phase, fa, fb, min(8u, left - blk * 8));
                 }
-            };
-            // main loop: 32 samples per iteration as ONE basic block: a chain of 32 dependent adds (the critical
-            // path of the whole path, 4 cycles each) with the loads, the sign test and lane 0's speculative phase
-            // stores issued in its shadow.  All increments non-negative (sign bits clear) => the chain is monotone
-            // and its last value bounds the rest, so p32 < 1 proves no wrap happened; a NaN anywhere lands in the
-            // last value and fails the test.  On failure the 32 samples are redone (the stores are overwritten).
-            const uint32_t nquad = nfull >> 2;
-            for (uint32_t q = 0; q < nquad; ++q) {
-                float4 fv[8];
+            } else {
+                // main path: the tile's 256 samples as straight-line code, 32 at a time: a chain of 32 dependent
+                // adds (the critical path of the whole path) plus 8 broadcast loads and one store.  A lone warp
+                // pays ~20 cycles for every taken branch, so there is no loop here and the only branch (the rare
+                // redo) is forward.  Increments are non-negative (k_frequency's tile flag), so the chain is
+                // monotone and its last value bounds the rest: p32 < 1 proves no wrap happened.
 #pragma unroll
-                for (int i = 0; i < 8; ++i) fv[i] = *reinterpret_cast<const float4*>(f + q * 32 + i * 4);
-                float p = phase;
-                uint32_t signs = 0;
+                for (uint32_t q = 0; q < 8; ++q) {
+                    float4 fv[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float a0 = p;
-                    const float a1 = sadd(a0, fv[i].x), a2 = sadd(a1, fv[i].y), a3 = sadd(a2, fv[i].z);
-                    p = sadd(a3, fv[i].w);
-                    if (lane0) *reinterpret_cast<float4*>(pw + q * 32 + i * 4) = make_float4(a0, a1, a2, a3);
-                    signs |= __float_as_uint(fv[i].x) | __float_as_uint(fv[i].y) | __float_as_uint(fv[i].z) |
-                             __float_as_uint(fv[i].w);
-                }
-                if ((int)signs >= 0 && p < 1.0f) {
-                    phase = p;
-                } else { // a carrier wrap inside these 32 samples: redo them 8 at a time
-#pragma unroll 1
-                    for (uint32_t b = 0; b < 4; ++b) block8(q * 4 + b);
-                }
-            }
-            uint32_t blk = nquad * 4;
-#pragma unroll 1
-            for (; blk < nfull; ++blk) block8(blk);
-            if (blk < nblk) { // ragged tail of the utterance
-                const uint32_t valid = left - blk * 8;
-#pragma unroll 1
-                for (uint32_t k = 0; k < valid; ++k) {
-                    if (lane0) pw[blk * 8 + k] = phase;
-                    phase = sadd(phase, f[blk * 8 + k]);
-                    if (phase >= 1.0f) phase = ssub(phase, 1.0f);
+                    for (int i = 0; i < 8; ++i) fv[i] = lds128(fa_ + q * 128 + i * 16);
+                    float p = phase;
+                    float ps[4];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if ((i & 1) == 0) ps[i >> 1] = p;
+                        p = sadd(sadd(sadd(sadd(p, fv[i].x), fv[i].y), fv[i].z), fv[i].w);
+                    }
+                    if (lane0) sts128(pa_ + q * 16, ps[0], ps[1], ps[2], ps[3]);
+                    if (__builtin_expect(p < 1.0f, 1)) phase = p;
+                    else phase = phase_redo_quad(phase, fa_ + q * 128, pa_ + q * 16, lane0);
                 }
             }
             __syncwarp();
@@ -420,22 +453,26 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
             const int buf = tile & 1;
             mbar_wait(&s_full[slot][buf], (tile >> 1) & 1);
             const float* f = sF[slot][tile % PH_STAGES];
-            const float* pw = sP[slot][buf];
             const uint32_t b0 = tile * PH_TILE + lane * 8;
-            float4 fa, fb, pa, pb;
+            float4 fa, fb;
+            float p = 0.0f;
             if (b0 < n) {
                 fa = *reinterpret_cast<const float4*>(f + lane * 8);
                 fb = *reinterpret_cast<const float4*>(f + lane * 8 + 4);
-                pa = *reinterpret_cast<const float4*>(pw + lane * 8);
-                pb = *reinterpret_cast<const float4*>(pw + lane * 8 + 4);
+                p = sP[slot][buf][lane];
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[slot][buf]);   // both shared tiles are in registers now
             if (b0 < n) {
                 const float fv[8] = { fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w };
-                const float pv[8] = { pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w };
                 const uint32_t valid = min(8u, n - b0);
-                float s[8];
+                float pv[8], s[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {   // replay this block's 8 steps from its start phase  :520-525
+                    pv[k] = p;
+                    p = sadd(p, fv[k]);
+                    if (p >= 1.0f) p = ssub(p, 1.0f);
+                }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     s[k] = ssub(smul(2.0f, pv[k]), 1.0f);                               // :517 with polyblep = 0

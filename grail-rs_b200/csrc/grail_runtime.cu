@@ -125,7 +125,7 @@ struct grail_plan {
     // device
     float* d_elems = nullptr; SegRec* d_segs = nullptr; UttDev* d_utts = nullptr; ItemDev* d_items = nullptr;
     JitSchedDev* d_jscheds = nullptr; JitRec* d_jrecs = nullptr; float* d_F = nullptr; float* d_saw = nullptr;
-    float* d_phase_dbg = nullptr; uint32_t* d_err = nullptr;
+    float* d_phase_dbg = nullptr; uint32_t* d_err = nullptr; uint32_t* d_fflags = nullptr;
     void* d_out = nullptr; size_t d_out_bytes = 0; int d_out_format = -1;
     cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
     bool launched = false;
@@ -243,6 +243,7 @@ static PlanDev plan_dev(const grail_plan* pl, bool with_dbg)
     P.jscheds = pl->d_jscheds; P.jrecs = pl->d_jrecs; P.F = pl->d_F; P.saw = pl->d_saw;
     P.phase_dbg = with_dbg ? pl->d_phase_dbg : nullptr;
     P.err = pl->d_err;
+    P.fflags = pl->d_fflags;
     P.n_utts = pl->n_utts; P.n_items = pl->n_items; P.n_groups = pl->n_groups; P.n_jscheds = pl->n_jscheds;
     P.chunk_len = pl->chunk_len;
     P.warmup_nepers = (float)pl->ctx->warmup_nepers;
@@ -254,7 +255,7 @@ static void plan_release(grail_plan* pl)
     if (!pl) return;
     grail_ctx* ctx = pl->ctx;
     void* bufs[] = { pl->d_elems, pl->d_segs, pl->d_utts, pl->d_items, pl->d_jscheds, pl->d_jrecs, pl->d_F, pl->d_saw,
-                     pl->d_phase_dbg, pl->d_err, pl->d_out };
+                     pl->d_phase_dbg, pl->d_err, pl->d_out, pl->d_fflags };
     for (void* b : bufs) pool_free(ctx, b);
     for (auto& e : pl->ev)
         if (e) cudaEventDestroy(e);
@@ -301,7 +302,7 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
         U.out_off = total;
         U.f_off = f_words;
         total += (uint64_t)n;
-        f_words += ((uint64_t)n + 7) & ~7ull;
+        f_words += ((uint64_t)n + 255) & ~255ull;   // 256-aligned: k_frequency's 128-sample runs index the flag words
         n_max = std::max(n_max, U.n_samples);
         pl->out_offsets[u + 1] = total;
         // a formant whose amplitude is zero in every element contributes exactly 0 (v0 = 0 keeps the SVF at rest)
@@ -329,7 +330,7 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
         }
     }
     pl->total_samples = total;
-    pl->f_words = f_words + 8;
+    pl->f_words = f_words + 256;
     pl->nw = nw;
     uint64_t n_jrecs = 0;
     for (auto& js : pl->jscheds) {
@@ -371,15 +372,16 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
         for (uint32_t u = 0; u < n_utts; ++u) n += (pl->utts[u].n_samples + c - 1) / c;
         return n;
     };
-    const uint64_t cl_hi = ((uint64_t)std::max<uint32_t>(n_max, 32u) + 31) & ~31ull;
-    uint64_t lo = 1, hi = cl_hi / 32;   // in units of 32 samples
+    const uint64_t G = 256;             // chunk granularity (k_phase tiles, k_frequency runs, k_formant batches)
+    const uint64_t cl_hi = ((uint64_t)std::max<uint32_t>(n_max, 1u) + G - 1) / G * G;
+    uint64_t lo = 1, hi = cl_hi / G;
     while (lo < hi) {
         const uint64_t mid = (lo + hi) / 2;
-        if (items_at(mid * 32) <= target) hi = mid; else lo = mid + 1;
+        if (items_at(mid * G) <= target) hi = mid; else lo = mid + 1;
     }
-    uint64_t cl = lo * 32;
-    cl = std::max<uint64_t>(cl, (ctx->min_chunk + 31) & ~31u);
-    cl = std::min<uint64_t>(cl, std::max<uint64_t>((ctx->max_chunk + 31) & ~31u, 32));
+    uint64_t cl = lo * G;
+    cl = std::max<uint64_t>(cl, (ctx->min_chunk + G - 1) / G * G);
+    cl = std::min<uint64_t>(cl, std::max<uint64_t>((ctx->max_chunk + G - 1) / G * G, G));
     cl = std::min<uint64_t>(cl, cl_hi);
     pl->chunk_len = (uint32_t)cl;
 
@@ -426,6 +428,7 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
     PA(pl->d_jscheds, std::max<size_t>(pl->n_jscheds, 1) * sizeof(JitSchedDev));
     PA(pl->d_jrecs, std::max<size_t>(pl->n_jrecs, 1) * sizeof(JitRec));
     PA(pl->d_F, pl->f_words * sizeof(float));
+    PA(pl->d_fflags, (pl->f_words / 128 + 2) * sizeof(uint32_t));
     PA(pl->d_saw, std::max<uint64_t>(pl->saw_words, 8) * sizeof(float));
     PA(pl->d_err, 256);
     cudaStream_t s = ctx->stream;
