@@ -3,7 +3,7 @@
 //   k_jitter_schedule  exact wrap schedule of the value-noise phase clock      (src/lib.rs:242-251)
 //   k_frequency        bit-exact per-sample fundamental F_t                     (src/lib.rs:861-931, 753-763)
 //   k_phase_pair       bit-exact carrier phase + polyBLEP saw, two warps/utt    (src/lib.rs:503-525)
-//   k_formant<NW>      noise, low-pass, turbulence, SVF band-pass, formant sum  (src/lib.rs:528-577, 764-773)
+//   k_formant<NW,FPT>  noise, low-pass, turbulence, SVF band-pass, formant sum  (src/lib.rs:528-577, 764-773)
 //
 // Exactness classes: the clocks, the LCG streams, F_t, the carrier phase and the saw are
 // computed with strict, never-contracted f32 ops in the reference's order and are bit-identical to it.
@@ -495,18 +495,14 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: the dominant kernel.  CTA = one group of 32 work items (time chunks) x NW warps; warp w owns the
-// w-th active formant of each item's utterance, lane l owns chunk l.  Each lane replays the exact
+// K3: the dominant kernel.  CTA = one group of 32 work items (time chunks) x NW warps; warp w owns FPT
+// consecutive active formants of each item's utterance (they share the clocks, the noise and the saw), lane l
+// owns chunk l.  Each lane replays the exact
 // clocks literally, generates its formant's parameters, noise, low-pass and SVF in registers, and
 // leaves v1 in a shared tile; every 32 samples the CTA sums the tile over formants (reference order)
 // and writes 128-byte rows.  Filter state at a chunk start comes from a warm-up over the preceding
 // samples, long enough that the zero-state error has decayed by exp(-warmup_nepers).
 // ------------------------------------------------------------------------------------------------
-struct FormantSeg {
-    float x[6], d[6];  // parameter = x + alpha * d   (d = y - x)
-    float inv_bl;
-};
-
 __device__ __forceinline__ void seg_endpoints(const float* ue, uint32_t p, uint32_t n_elems, int fi, float* x, float* y,
                                               float* blend_len)
 {
@@ -529,17 +525,6 @@ __device__ __forceinline__ void seg_endpoints(const float* ue, uint32_t p, uint3
     }
     if (!c_on) x[P_AMP] = 0.0f; // b.copy_silent().blend(b, alpha)   :911
     if (!b_on) y[P_AMP] = 0.0f; // c.blend(c.copy_silent(), alpha)   :920
-}
-
-__device__ __forceinline__ FormantSeg load_formant_seg(const float* ue, uint32_t p, uint32_t n_elems, int fi)
-{
-    float x[6], y[6], bl;
-    seg_endpoints(ue, p, n_elems, fi, x, y, &bl);
-    FormantSeg s;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) { s.x[k] = x[k]; s.d[k] = y[k] - x[k]; }
-    s.inv_bl = 1.0f / bl;
-    return s;
 }
 
 // tan(pi x) approximation of src/lib.rs:63-70, as numerator / denominator
@@ -606,22 +591,32 @@ __device__ uint32_t warmup_len(const float* ue, const SegRec* segs, uint32_t n_e
     }
 }
 
-struct LaneState {
-    // clocks
-    float time, jph;
-    uint32_t p;
-    // noise streams
-    uint32_t s_noise, s_ff, s_amp;   // LCG states: synth noise, next formant_freq draw, next formant_amp draw
-    uint32_t jw;                      // jitter wraps so far
-    float ffc, ffd, ampc, ampd;       // value-noise current and (next - current)
-    // filters
-    float a, b, c;
+// LCG^8 as compile-time constants (the 8 formant draws of one value-noise refill are 8 apart, src/lib.rs:301)
+constexpr uint32_t lcg_pow_a(int n) { uint32_t a = 1; for (int i = 0; i < n; ++i) a *= LCG_A; return a; }
+constexpr uint32_t lcg_pow_c(int n) { uint32_t c = 0; for (int i = 0; i < n; ++i) c = c * LCG_A + LCG_C; return c; }
+constexpr uint32_t LCG8_A = lcg_pow_a(8), LCG8_C = lcg_pow_c(8);
+
+// One formant of one lane.  Every per-sample parameter is one or two FMAs of the two slowly varying scalars
+//   alpha (Sequencer blend position, src/lib.rs:899) and jph (value-noise phase, :291):
+//   formant_freq = ff0 + alpha*ff1 + jph*ff2       (blend :407 + jitter :764, the jitter lerp folded in)
+//   formant_amp  = (am0 + alpha*am1) * (aj0 + jph*aj1)                          (blend :412 + jitter :768-773)
+//   1 - smooth, bw, breath, turb = x0 + alpha*x1                                        (blend :408-411)
+// The folded constants change only at a phoneme hand-over or a value-noise wrap.
+struct FormantLane {
+    float ff0, ff1, ff2, xff;
+    float bw0, bw1, om0, om1, br0, br1, tb0, tb1, am0, am1;
+    float aj0, aj1;
+    uint32_t s_ff, s_amp;   // LCG states of the "next" draws of formant_freq_noise[fi] / formant_amp_noise[fi]
+    float a, b, c;          // low-pass state, SVF ic1eq, ic2eq
+    int fi;                 // formant index, -1 if this slot is unused
 };
 
-constexpr int FORMANT_WARPS_PER_SM = 32;   // 64 registers per lane
+template <int FPT> struct FormantCfg { static constexpr int warps_per_sm = 32; };   // 64 registers per lane
+template <> struct FormantCfg<2> { static constexpr int warps_per_sm = 20; };       // ~100 registers per lane
 
-template <int NW>
-__global__ void __launch_bounds__(NW * 32, FORMANT_WARPS_PER_SM / NW) k_formant(PlanDev P, void* __restrict__ out, int format)
+template <int NW, int FPT>
+__global__ void __launch_bounds__(NW * 32, FormantCfg<FPT>::warps_per_sm / NW)
+k_formant(PlanDev P, void* __restrict__ out, int format)
 {
     __shared__ float part[NW][32][33];
     __shared__ unsigned long long row_out[32];
@@ -635,8 +630,6 @@ __global__ void __launch_bounds__(NW * 32, FORMANT_WARPS_PER_SM / NW) k_formant(
     it.utt = 0; it.n0 = 0; it.len = 0; it.pad = 0;
     if (have) it = P.items[item_id];
     const UttDev& U = P.utts[it.utt];
-    const int fi = (have && (uint32_t)w < U.n_active) ? (int)U.active[w] : -1;
-    const bool on = fi >= 0 && it.len > 0;
     if (w == 0) {
         row_out[lane] = U.out_off + it.n0;
         row_len[lane] = it.len;
@@ -651,109 +644,161 @@ __global__ void __launch_bounds__(NW * 32, FORMANT_WARPS_PER_SM / NW) k_formant(
     const float jinc = U.voice.jitter_frequency;
     const float dff = U.voice.jitter_delta_formant_frequency;
     const float hda = 0.5f * U.voice.jitter_delta_amplitude;   // :769
-    const float one_m_hda = 1.0f - hda;
+    const float quiet_t = 9.0f * dt, quiet_j = 1.0f - 9.0f * jinc;
+    const uint32_t jseed = U.voice.jitter_seed;
 
-    // ---- warm-up depth: per lane, then the warp maximum so the whole warp walks the same rows
+    FormantLane L[FPT];
+    bool on = false;
+#pragma unroll
+    for (int j = 0; j < FPT; ++j) {
+        const uint32_t slot = (uint32_t)(w * FPT + j);
+        L[j].fi = (have && it.len > 0 && slot < U.n_active) ? (int)U.active[slot] : -1;
+        on |= L[j].fi >= 0;
+        // an unused slot runs SynthesisElem::silent() parameters with zero amplitude: it contributes exactly 0
+        L[j].ff0 = 0.25f; L[j].ff1 = 0.f; L[j].ff2 = 0.f; L[j].xff = 0.25f;
+        L[j].bw0 = 0.25f; L[j].bw1 = 0.f; L[j].om0 = 0.75f; L[j].om1 = 0.f;
+        L[j].br0 = L[j].br1 = L[j].tb0 = L[j].tb1 = L[j].am0 = L[j].am1 = 0.f;
+        L[j].aj0 = 1.f; L[j].aj1 = 0.f;
+        L[j].s_ff = L[j].s_amp = 0u;
+        L[j].a = L[j].b = L[j].c = 0.f;
+    }
+
+    // ---- warm-up depth: per lane (max over its formants), then the warp maximum so the warp walks the same rows
     uint32_t wlen = 0;
-    if (on && it.n0 > 0) wlen = warmup_len(ue, segs, n_elems, it.n0, fi, dff, P.warmup_nepers);
+    if (on && it.n0 > 0) {
+#pragma unroll
+        for (int j = 0; j < FPT; ++j)
+            if (L[j].fi >= 0) wlen = max(wlen, warmup_len(ue, segs, n_elems, it.n0, L[j].fi, dff, P.warmup_nepers));
+    }
     uint32_t wmax = wlen;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    const uint32_t wmine = min(wmax, it.n0);      // multiple of 8 (n0 is a multiple of 32)
+    const uint32_t wmine = min(wmax, it.n0);      // multiple of 8 (n0 is a multiple of 256)
     const uint32_t ns = it.n0 - wmine;            // first sample this lane computes
 
-    // ---- lane state at sample ns
-    LaneState st;
-    FormantSeg seg;
-    uint32_t lcg8a, lcg8c;
-    lcg_pow(8, &lcg8a, &lcg8c);
-    st.a = st.b = st.c = 0.0f;
-    st.time = 0.0f; st.jph = 0.0f; st.p = 0; st.jw = 0;
-    st.s_noise = st.s_ff = st.s_amp = 0;
-    st.ffc = st.ffd = st.ampc = st.ampd = 0.0f;
+    // ---- shared (per lane) clocks and noise at sample ns
+    float time = 0.f, jph = 0.f, inv_bl = 0.f;
+    uint32_t p = 0, jw = 0, s_noise = 0;
+
+    // (re)load the blend endpoints of phoneme p for every formant of this lane  (:891-931)
+    auto load_segment = [&]() {
+        float bl = 1.0f;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { seg.x[k] = 0.0f; seg.d[k] = 0.0f; }
-    seg.inv_bl = 0.0f;
+        for (int j = 0; j < FPT; ++j) {
+            if (L[j].fi < 0) continue;
+            float x[6], y[6];
+            seg_endpoints(ue, p, n_elems, L[j].fi, x, y, &bl);
+            L[j].ff0 += x[P_FF] - L[j].xff;            // keep the folded jitter term, swap the base
+            L[j].xff = x[P_FF];
+            L[j].ff1 = y[P_FF] - x[P_FF];
+            L[j].bw0 = x[P_BW]; L[j].bw1 = y[P_BW] - x[P_BW];
+            L[j].om0 = 1.0f - x[P_SM]; L[j].om1 = x[P_SM] - y[P_SM];
+            L[j].br0 = x[P_BR]; L[j].br1 = y[P_BR] - x[P_BR];
+            L[j].tb0 = x[P_TB]; L[j].tb1 = y[P_TB] - x[P_TB];
+            L[j].am0 = x[P_AMP]; L[j].am1 = y[P_AMP] - x[P_AMP];
+        }
+        inv_bl = 1.0f / bl;
+    };
+    // fold the value-noise (current, next) pairs into the per-sample constants  (:289-306, :764-773)
+    auto fold_jitter = [&](int j, float ffc, float ffn, float amc, float amn) {
+        L[j].ff0 = fmaf(dff, ffc, L[j].xff);
+        L[j].ff2 = dff * (ffn - ffc);
+        L[j].aj0 = (1.0f - hda) - hda * amc;           // 1 - (n + 1) * (0.5 * delta_amplitude)
+        L[j].aj1 = -hda * (amn - amc);
+    };
+
     if (on) {
-        st.p = last_le(n_elems, [&](uint32_t i) { return segs[i].start; }, (int64_t)ns);
-        st.time = clock_desc_run(segs[st.p].time0, dt, ns - segs[st.p].start).x;
-        seg = load_formant_seg(ue, st.p, n_elems, fi);
+        p = last_le(n_elems, [&](uint32_t i) { return segs[i].start; }, (int64_t)ns);
+        time = clock_desc_run(segs[p].time0, dt, ns - segs[p].start).x;
         const JitSchedDev& JS = P.jscheds[U.jit_sched];
         const JitRec* recs = P.jrecs + JS.rec_first;
-        st.jw = last_le(JS.n_recs, [&](uint32_t i) { return recs[i].n; }, (int64_t)ns);
-        st.jph = clock_asc_run(recs[st.jw].phase, jinc, (uint64_t)((int64_t)ns - recs[st.jw].n)).x;
-        const uint32_t seed = U.voice.jitter_seed;
-        const float c0 = lcg_float(lcg_jump(seed, jit_arr_cur_idx(0, fi, st.jw)));
-        st.s_ff = lcg_jump(seed, jit_arr_next_idx(0, fi, st.jw));
-        st.ffc = c0; st.ffd = lcg_float(st.s_ff) - c0;
-        const float c1 = lcg_float(lcg_jump(seed, jit_arr_cur_idx(1, fi, st.jw)));
-        st.s_amp = lcg_jump(seed, jit_arr_next_idx(1, fi, st.jw));
-        st.ampc = c1; st.ampd = lcg_float(st.s_amp) - c1;
-        st.s_noise = lcg_jump(U.voice.synth_seed, ns);   // noise of sample n is draw n+1  (:528)
+        jw = last_le(JS.n_recs, [&](uint32_t i) { return recs[i].n; }, (int64_t)ns);
+        jph = clock_asc_run(recs[jw].phase, jinc, (uint64_t)((int64_t)ns - recs[jw].n)).x;
+        s_noise = lcg_jump(U.voice.synth_seed, ns);   // noise of sample n is draw n+1  (:528)
+#pragma unroll
+        for (int j = 0; j < FPT; ++j) {
+            if (L[j].fi < 0) continue;
+            const float c0 = lcg_float(lcg_jump(jseed, jit_arr_cur_idx(0, L[j].fi, jw)));
+            L[j].s_ff = lcg_jump(jseed, jit_arr_next_idx(0, L[j].fi, jw));
+            const float c1 = lcg_float(lcg_jump(jseed, jit_arr_cur_idx(1, L[j].fi, jw)));
+            L[j].s_amp = lcg_jump(jseed, jit_arr_next_idx(1, L[j].fi, jw));
+            L[j].xff = 0.f;
+            fold_jitter(j, c0, lcg_float(L[j].s_ff), c1, lcg_float(L[j].s_amp));
+            L[j].xff = 0.f; L[j].ff0 = dff * c0;      // base added by load_segment below
+        }
+        load_segment();
     }
 
-    // one sample of this lane's formant; returns v1 (band-pass output, :566)
+    // one sample: all formants of this lane; returns their v1 sum (band-pass outputs, :566)
     auto sample = [&](float saw) -> float {
-        const float alpha = fminf(st.time * seg.inv_bl, 1.0f);               // :899
-        st.s_noise = st.s_noise * LCG_A + LCG_C;                             // :40
-        const float nz = fmaf(__uint_as_float((st.s_noise >> 9) | 0x3F800000u), 2.0f, -3.0f);
-        // parameters: Sequencer blend (:404-414) then Jitter (:764-773)
-        const float n1 = fmaf(st.jph, st.ffd, st.ffc);
-        const float n2 = fmaf(st.jph, st.ampd, st.ampc);
-        const float ff = fmaf(n1, dff, fmaf(alpha, seg.d[P_FF], seg.x[P_FF]));
-        const float bw = fmaf(alpha, seg.d[P_BW], seg.x[P_BW]);
-        const float sm = fmaf(alpha, seg.d[P_SM], seg.x[P_SM]);
-        const float br = fmaf(alpha, seg.d[P_BR], seg.x[P_BR]);
-        const float tb = fmaf(alpha, seg.d[P_TB], seg.x[P_TB]);
-        const float amp = fmaf(alpha, seg.d[P_AMP], seg.x[P_AMP]) * fmaf(n2, -hda, one_m_hda);
-        // source: breath mix, one-pole low-pass, turbulence, amplitude (:531-550)
-        const float nw = fmaf(br, nz - saw, saw);
-        const float o = 1.0f - sm, o2 = o * o;
-        const float a5 = o2 * o2 * o;                                        // exp_approx :75-82
-        st.a = fmaf(1.0f - a5, nw - st.a, st.a);                             // :538
-        const float v0 = st.a * fmaf(tb, nz - 1.0f, 1.0f) * amp;             // :544-550
-        // SVF coefficients (:555-562)
-        float num, den;
-        tan_nd(ff, &num, &den);
-        const float g = num * frcp(den);
-        const float k = bw * frcp(ff);
-        const float a1 = frcp(fmaf(g, g + k, 1.0f));
-        const float a2 = g * a1;
-        const float a3 = g * a2;
-        // SVF tick (:565-571)
-        const float v3 = v0 - st.c;
-        const float v1 = fmaf(a1, st.b, a2 * v3);
-        const float v2 = fmaf(a3, v3, fmaf(a2, st.b, st.c));
-        st.b = fmaf(2.0f, v1, -st.b);
-        st.c = fmaf(2.0f, v2, -st.c);
-        return v1;
+        const float alpha = fminf(time * inv_bl, 1.0f);                      // :899
+        s_noise = s_noise * LCG_A + LCG_C;                                   // :40
+        const float nz = fmaf(__uint_as_float((s_noise >> 9) | 0x3F800000u), 2.0f, -3.0f);
+        const float d1 = nz - saw, nzm1 = nz - 1.0f;
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < FPT; ++j) {
+            FormantLane& F = L[j];
+            const float ff = fmaf(jph, F.ff2, fmaf(alpha, F.ff1, F.ff0));
+            const float bw = fmaf(alpha, F.bw1, F.bw0);
+            const float o = fmaf(alpha, F.om1, F.om0);                        // 1 - smooth
+            const float br = fmaf(alpha, F.br1, F.br0);
+            const float tb = fmaf(alpha, F.tb1, F.tb0);
+            const float amp = fmaf(alpha, F.am1, F.am0) * fmaf(jph, F.aj1, F.aj0);
+            // source: breath mix, one-pole low-pass, turbulence, amplitude (:531-550)
+            const float nw = fmaf(br, d1, saw);
+            const float o2 = o * o;
+            const float a5 = o2 * o2 * o;                                     // exp_approx :75-82
+            F.a = fmaf(1.0f - a5, nw - F.a, F.a);                             // :538
+            const float v0 = F.a * fmaf(tb, nzm1, 1.0f) * amp;                // :544-550
+            // SVF coefficients (:555-562)
+            float num, den;
+            tan_nd(ff, &num, &den);
+            const float g = num * frcp(den);
+            const float kq = bw * frcp(ff);
+            const float a1 = frcp(fmaf(g, g + kq, 1.0f));
+            const float a2 = g * a1;
+            const float a3 = g * a2;
+            // SVF tick (:565-571)
+            const float v3 = v0 - F.c;
+            const float v1 = fmaf(a1, F.b, a2 * v3);
+            const float v2 = fmaf(a3, v3, fmaf(a2, F.b, F.c));
+            F.b = fmaf(2.0f, v1, -F.b);
+            F.c = fmaf(2.0f, v2, -F.c);
+            acc += v1;
+        }
+        return acc;
     };
     // clock advance with the rare events handled (phoneme hand-over, value-noise wrap)
     auto advance_slow = [&]() {
-        st.time = __fadd_rn(st.time, ndt);                                   // :861
-        if (st.time < 0.0f) {                                                // :864
-            ++st.p;
-            if (st.p < n_elems) {
-                st.time = __fadd_rn(st.time, ue[(size_t)st.p * SEQ_WORDS + SE_LEN]);   // :873
-                seg = load_formant_seg(ue, st.p, n_elems, fi);
+        time = __fadd_rn(time, ndt);                                         // :861
+        if (time < 0.0f) {                                                   // :864
+            ++p;
+            if (p < n_elems) {
+                time = __fadd_rn(time, ue[(size_t)p * SEQ_WORDS + SE_LEN]);  // :873
+                load_segment();
             }
         }
-        st.jph = __fadd_rn(st.jph, jinc);                                    // :291
-        if (st.jph > 1.0f) {                                                 // :294
-            st.jph = __fadd_rn(st.jph, -1.0f);
-            ++st.jw;
-            const float nf = lcg_float(st.s_ff), na = lcg_float(st.s_amp);   // old next becomes current
-            if (st.jw == 1) {
-                st.s_ff = lcg_jump(U.voice.jitter_seed, jit_arr_next_idx(0, fi, 1));
-                st.s_amp = lcg_jump(U.voice.jitter_seed, jit_arr_next_idx(1, fi, 1));
-            } else {
-                st.s_ff = lcg8a * st.s_ff + lcg8c;                           // 8 draws per wrap :301
-                st.s_amp = lcg8a * st.s_amp + lcg8c;
+        jph = __fadd_rn(jph, jinc);                                          // :291
+        if (jph > 1.0f) {                                                    // :294
+            jph = __fadd_rn(jph, -1.0f);
+            ++jw;
+#pragma unroll
+            for (int j = 0; j < FPT; ++j) {
+                if (L[j].fi < 0) continue;
+                const float nf = lcg_float(L[j].s_ff), na_ = lcg_float(L[j].s_amp);   // old next becomes current
+                if (jw == 1) {
+                    L[j].s_ff = lcg_jump(jseed, jit_arr_next_idx(0, L[j].fi, 1));
+                    L[j].s_amp = lcg_jump(jseed, jit_arr_next_idx(1, L[j].fi, 1));
+                } else {
+                    L[j].s_ff = LCG8_A * L[j].s_ff + LCG8_C;                 // 8 draws per refill :301
+                    L[j].s_amp = LCG8_A * L[j].s_amp + LCG8_C;
+                }
+                fold_jitter(j, nf, lcg_float(L[j].s_ff), na_, lcg_float(L[j].s_amp));
             }
-            st.ffc = nf; st.ffd = lcg_float(st.s_ff) - nf;
-            st.ampc = na; st.ampd = lcg_float(st.s_amp) - na;
         }
     };
+
     __syncthreads();   // row_out / row_len visible
     uint32_t lmax = 0;
 #pragma unroll 1
@@ -763,7 +808,6 @@ __global__ void __launch_bounds__(NW * 32, FORMANT_WARPS_PER_SM / NW) k_formant(
     // at r == 0, into this lane's own chunk) is a pointer reset every CL samples
     uint32_t src_item = U.item_first + ns / CL, src_j = ns % CL;
     const float4* sp = reinterpret_cast<const float4*>(P.saw + saw_index(src_item, src_j, CL));
-
     // saw values are fetched one iteration ahead (register double buffer) so the L2 latency of the
     // coalesced 128-bit loads is covered by a whole block of arithmetic
     float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
@@ -789,15 +833,15 @@ __global__ void __launch_bounds__(NW * 32, FORMANT_WARPS_PER_SM / NW) k_formant(
         const float4 sa = na, sb = nb;
         if (active_at(r + 8)) fetch();
         if (act) {
-            const bool quiet = (st.time > 9.0f * dt) && (st.jph + 9.0f * jinc < 1.0f);
+            const bool quiet = (time > quiet_t) && (jph < quiet_j);
             if (quiet) { // no hand-over and no wrap can fall inside: branch-free literal clocks
                 const float s8[8] = { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w };
                 float v[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     v[k] = sample(s8[k]);
-                    st.time = __fadd_rn(st.time, ndt);
-                    st.jph = __fadd_rn(st.jph, jinc);
+                    time = __fadd_rn(time, ndt);
+                    jph = __fadd_rn(jph, jinc);
                 }
                 if (r >= 0) {
 #pragma unroll
@@ -821,7 +865,7 @@ __global__ void __launch_bounds__(NW * 32, FORMANT_WARPS_PER_SM / NW) k_formant(
         if (r >= 0 && (r & 31) == 24) {
             const uint32_t base = (uint32_t)r - 24u;
             __syncthreads();
-            // rows w, w+NW, ...: sum the formants in index order (Array::sum is a left fold, :123), scale (:574)
+            // rows w, w+NW, ...: sum the formant groups in index order (Array::sum, :123), scale (:574)
             for (int row = w; row < 32; row += NW) {
                 const uint32_t rl = row_len[row];
                 if (base + lane < rl) {

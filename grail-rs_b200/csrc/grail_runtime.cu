@@ -40,6 +40,7 @@ struct grail_ctx {
     uint32_t min_chunk = 2048;
     uint32_t max_chunk = 1u << 22;
     int      debug_taps = 0;
+    int      formants_per_lane = 2;  // 1 or 2 formants of an utterance share one lane's clocks, noise and saw
     // pinned staging for pageable D2H
     void*    stage[2] = { nullptr, nullptr };
     size_t   stage_bytes = 0;
@@ -114,7 +115,7 @@ static void pool_free(grail_ctx* ctx, void* p)
 // ------------------------------------------------------------------------------------------------
 struct grail_plan {
     grail_ctx* ctx = nullptr;
-    uint32_t n_utts = 0, n_elems = 0, n_items = 0, n_groups = 0, n_jscheds = 0, n_jrecs = 0, nw = 1;
+    uint32_t n_utts = 0, n_elems = 0, n_items = 0, n_groups = 0, n_jscheds = 0, n_jrecs = 0, nw = 1, fpt = 1;
     uint32_t chunk_len = 0;
     uint64_t total_samples = 0, f_words = 0, saw_words = 0;
     std::vector<UttDev>      utts;       // host copies (original utterance order)
@@ -210,29 +211,60 @@ static int validate_inputs(grail_ctx* ctx, const grail_seq_elem* elems, const ui
     return GRAIL_OK;
 }
 
-template <int NW>
+template <int NW, int FPT>
 static void launch_formant(const PlanDev& P, void* out, int format, cudaStream_t s)
 {
-    k_formant<NW><<<P.n_groups, NW * 32, 0, s>>>(P, out, format);
+    k_formant<NW, FPT><<<P.n_groups, NW * 32, 0, s>>>(P, out, format);
 }
-template <int NW>
+template <int NW, int FPT>
 static int formant_occupancy()
 {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_formant<NW>, NW * 32, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_formant<NW, FPT>, NW * 32, 0);
     return nb;
 }
-static int formant_occupancy_nw(int nw)
+// NW = warps per CTA (formant groups), FPT = formants per lane
+static int formant_occupancy_of(int nw, int fpt)
 {
+    if (fpt == 2) {
+        switch (nw) {
+        case 1: return formant_occupancy<1, 2>();
+        case 2: return formant_occupancy<2, 2>();
+        case 3: return formant_occupancy<3, 2>();
+        default: return formant_occupancy<4, 2>();
+        }
+    }
     switch (nw) {
-    case 1: return formant_occupancy<1>();
-    case 2: return formant_occupancy<2>();
-    case 3: return formant_occupancy<3>();
-    case 4: return formant_occupancy<4>();
-    case 5: return formant_occupancy<5>();
-    case 6: return formant_occupancy<6>();
-    case 7: return formant_occupancy<7>();
-    default: return formant_occupancy<8>();
+    case 1: return formant_occupancy<1, 1>();
+    case 2: return formant_occupancy<2, 1>();
+    case 3: return formant_occupancy<3, 1>();
+    case 4: return formant_occupancy<4, 1>();
+    case 5: return formant_occupancy<5, 1>();
+    case 6: return formant_occupancy<6, 1>();
+    case 7: return formant_occupancy<7, 1>();
+    default: return formant_occupancy<8, 1>();
+    }
+}
+static void launch_formant_of(int nw, int fpt, const PlanDev& P, void* out, int format, cudaStream_t s)
+{
+    if (fpt == 2) {
+        switch (nw) {
+        case 1: launch_formant<1, 2>(P, out, format, s); break;
+        case 2: launch_formant<2, 2>(P, out, format, s); break;
+        case 3: launch_formant<3, 2>(P, out, format, s); break;
+        default: launch_formant<4, 2>(P, out, format, s); break;
+        }
+        return;
+    }
+    switch (nw) {
+    case 1: launch_formant<1, 1>(P, out, format, s); break;
+    case 2: launch_formant<2, 1>(P, out, format, s); break;
+    case 3: launch_formant<3, 1>(P, out, format, s); break;
+    case 4: launch_formant<4, 1>(P, out, format, s); break;
+    case 5: launch_formant<5, 1>(P, out, format, s); break;
+    case 6: launch_formant<6, 1>(P, out, format, s); break;
+    case 7: launch_formant<7, 1>(P, out, format, s); break;
+    default: launch_formant<8, 1>(P, out, format, s); break;
     }
 }
 
@@ -331,7 +363,9 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
     }
     pl->total_samples = total;
     pl->f_words = f_words + 256;
-    pl->nw = nw;
+    pl->fpt = (uint32_t)ctx->formants_per_lane;
+    pl->nw = (nw + pl->fpt - 1) / pl->fpt;   // warps per CTA: ceil(active formants / formants per lane)
+    nw = pl->nw;
     uint64_t n_jrecs = 0;
     for (auto& js : pl->jscheds) {
         js.rec_first = (uint32_t)n_jrecs;
@@ -361,7 +395,7 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
     // ---- chunking: aim for one resident wave of k_formant CTAs (32 chunks each)
     uint64_t target = ctx->target_items;
     if (target == 0) {
-        int occ = formant_occupancy_nw((int)nw);
+        int occ = formant_occupancy_of((int)nw, (int)pl->fpt);
         if (occ < 1) occ = 1;
         target = (uint64_t)ctx->prop.multiProcessorCount * (uint64_t)occ * 32ull;
     }
@@ -475,16 +509,7 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
     }
     CU(ctx, cudaEventRecord(pl->ev[3], s));
     if (pl->n_items && formant) {
-        switch (pl->nw) {
-        case 1: launch_formant<1>(P, d_out, format, s); break;
-        case 2: launch_formant<2>(P, d_out, format, s); break;
-        case 3: launch_formant<3>(P, d_out, format, s); break;
-        case 4: launch_formant<4>(P, d_out, format, s); break;
-        case 5: launch_formant<5>(P, d_out, format, s); break;
-        case 6: launch_formant<6>(P, d_out, format, s); break;
-        case 7: launch_formant<7>(P, d_out, format, s); break;
-        default: launch_formant<8>(P, d_out, format, s); break;
-        }
+        launch_formant_of((int)pl->nw, (int)pl->fpt, P, d_out, format, s);
         pl->last_launches++;
     }
     CU(ctx, cudaEventRecord(pl->ev[4], s));
@@ -601,6 +626,9 @@ int grail_cuda_set_option(grail_ctx* ctx, const char* key, double value)
         ctx->min_chunk = std::max(32u, (uint32_t)value);
     } else if (!strcmp(key, "max_chunk")) {
         ctx->max_chunk = std::max(32u, (uint32_t)value);
+    } else if (!strcmp(key, "formants_per_lane")) {
+        if (value != 1.0 && value != 2.0) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "formants_per_lane must be 1 or 2");
+        ctx->formants_per_lane = (int)value;
     } else if (!strcmp(key, "debug_taps")) {
         ctx->debug_taps = value != 0.0;
     } else {
