@@ -564,7 +564,7 @@ __device__ float seg_decay_rate(const float* ue, uint32_t p, uint32_t n_elems, i
     r = fminf(r, decay_rate(y[P_FF] + dff, y[P_BW], y[P_SM]));
     r = fminf(r, decay_rate(x[P_FF] - dff, y[P_BW], x[P_SM]));
     r = fminf(r, decay_rate(y[P_FF] + dff, x[P_BW], y[P_SM]));
-    return 0.9f * r;
+    return r;
 }
 
 // samples of history needed before n0 so that a zero-state start has decayed by exp(-need)
@@ -618,7 +618,9 @@ template <int NW, int FPT>
 __global__ void __launch_bounds__(NW * 32, FormantCfg<FPT>::warps_per_sm / NW)
 k_formant(PlanDev P, void* __restrict__ out, int format)
 {
-    __shared__ float part[NW][32][33];
+    // partial sums: [formant group][chunk row][32 samples], rows padded to 36 floats so that both the per-lane
+    // 128-bit row writes and the 8-lanes-per-row 128-bit reads of the reduction are bank-conflict free
+    __shared__ __align__(16) float part[NW][32][36];
     __shared__ unsigned long long row_out[32];
     __shared__ uint32_t row_len[32];
 
@@ -644,7 +646,7 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
     const float jinc = U.voice.jitter_frequency;
     const float dff = U.voice.jitter_delta_formant_frequency;
     const float hda = 0.5f * U.voice.jitter_delta_amplitude;   // :769
-    const float quiet_t = 9.0f * dt, quiet_j = 1.0f - 9.0f * jinc;
+    const float quiet_t = 9.0f * dt;
     const uint32_t jseed = U.voice.jitter_seed;
 
     FormantLane L[FPT];
@@ -769,33 +771,31 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
         }
         return acc;
     };
-    // clock advance with the rare events handled (phoneme hand-over, value-noise wrap)
-    auto advance_slow = [&]() {
-        time = __fadd_rn(time, ndt);                                         // :861
-        if (time < 0.0f) {                                                   // :864
-            ++p;
-            if (p < n_elems) {
-                time = __fadd_rn(time, ue[(size_t)p * SEQ_WORDS + SE_LEN]);  // :873
-                load_segment();
-            }
-        }
-        jph = __fadd_rn(jph, jinc);                                          // :291
-        if (jph > 1.0f) {                                                    // :294
-            jph = __fadd_rn(jph, -1.0f);
-            ++jw;
+    // value-noise wrap: current <- next, draw the new next, refold  (:294-301).  Small, so it is inlined after
+    // every sample of the unrolled block; lanes hit it at different samples (one lane in ~2756 per sample).
+    auto jitter_wrap = [&]() {
+        jph = __fadd_rn(jph, -1.0f);
+        ++jw;
 #pragma unroll
-            for (int j = 0; j < FPT; ++j) {
-                if (L[j].fi < 0) continue;
-                const float nf = lcg_float(L[j].s_ff), na_ = lcg_float(L[j].s_amp);   // old next becomes current
-                if (jw == 1) {
-                    L[j].s_ff = lcg_jump(jseed, jit_arr_next_idx(0, L[j].fi, 1));
-                    L[j].s_amp = lcg_jump(jseed, jit_arr_next_idx(1, L[j].fi, 1));
-                } else {
-                    L[j].s_ff = LCG8_A * L[j].s_ff + LCG8_C;                 // 8 draws per refill :301
-                    L[j].s_amp = LCG8_A * L[j].s_amp + LCG8_C;
-                }
-                fold_jitter(j, nf, lcg_float(L[j].s_ff), na_, lcg_float(L[j].s_amp));
+        for (int j = 0; j < FPT; ++j) {
+            if (L[j].fi < 0) continue;
+            const float nf = lcg_float(L[j].s_ff), na_ = lcg_float(L[j].s_amp);   // old next becomes current
+            if (jw == 1) {
+                L[j].s_ff = lcg_jump(jseed, jit_arr_next_idx(0, L[j].fi, 1));
+                L[j].s_amp = lcg_jump(jseed, jit_arr_next_idx(1, L[j].fi, 1));
+            } else {
+                L[j].s_ff = LCG8_A * L[j].s_ff + LCG8_C;                     // 8 draws per refill :301
+                L[j].s_amp = LCG8_A * L[j].s_amp + LCG8_C;
             }
+            fold_jitter(j, nf, lcg_float(L[j].s_ff), na_, lcg_float(L[j].s_amp));
+        }
+    };
+    // phoneme hand-over (:864-888): rare (once per phoneme per lane) and large, handled in the per-sample loop
+    auto handover = [&]() {
+        ++p;
+        if (p < n_elems) {
+            time = __fadd_rn(time, ue[(size_t)p * SEQ_WORDS + SE_LEN]);      // :873
+            load_segment();
         }
     };
 
@@ -823,68 +823,101 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
             sp += 64;
         }
     };
-    auto active_at = [&](int r) { return on && r >= -(int)wmine && r < (int)it.len; };
-    if (active_at(-(int)wmax)) fetch();
+    // this lane computes r in [r_lo, r_hi): its warm-up then its chunk (empty for an idle lane)
+    const int r_lo = on ? -(int)wmine : 0x7fffffff;
+    const int r_hi = on ? (int)it.len : (int)0x80000000;
+    if (-(int)wmax >= r_lo && -(int)wmax < r_hi) fetch();
+    const unsigned part_a = (unsigned)__cvta_generic_to_shared(&part[w][lane][0]);
 
     // ---- one loop over [-wmax, lmax) in steps of 8: warm-up (r < 0, no output) then the chunk itself
     for (int r = -(int)wmax; r < (int)lmax; r += 8) {
-        const bool act = active_at(r);
-        float* dst = &part[w][lane][r & 31];
+        const bool act = r >= r_lo && r < r_hi;
         const float4 sa = na, sb = nb;
-        if (active_at(r + 8)) fetch();
+        if (r + 8 >= r_lo && r + 8 < r_hi) fetch();
+        float v[8];
         if (act) {
-            const bool quiet = (time > quiet_t) && (jph < quiet_j);
-            if (quiet) { // no hand-over and no wrap can fall inside: branch-free literal clocks
+            if (time > quiet_t) {
+                // no hand-over can fall inside these 8 samples: literal clocks, one inlined wrap test per sample
                 const float s8[8] = { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w };
-                float v[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     v[k] = sample(s8[k]);
-                    time = __fadd_rn(time, ndt);
-                    jph = __fadd_rn(jph, jinc);
-                }
-                if (r >= 0) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) dst[k] = v[k];
+                    time = __fadd_rn(time, ndt);                             // :861
+                    jph = __fadd_rn(jph, jinc);                              // :291
+                    if (__builtin_expect(jph > 1.0f, 0)) jitter_wrap();      // :294
                 }
             } else {
+                // the phoneme's last samples: generic per-sample loop (results parked in the smem row)
 #pragma unroll 1
                 for (int k = 0; k < 8; ++k) {
                     const float4 q = k < 4 ? sa : sb;
                     const int kk = k & 3;
                     const float s = kk == 0 ? q.x : (kk == 1 ? q.y : (kk == 2 ? q.z : q.w));
-                    const float v = sample(s);
-                    advance_slow();
-                    if (r >= 0) dst[k] = v;
+                    const float vk = sample(s);
+                    time = __fadd_rn(time, ndt);
+                    if (time < 0.0f) handover();                             // :864
+                    jph = __fadd_rn(jph, jinc);
+                    if (jph > 1.0f) jitter_wrap();
+                    sts32(part_a + ((r & 31) + k) * 4, vk);
+                }
+                if (r >= 0) {
+                    const float4 t0 = lds128(part_a + (r & 31) * 4), t1 = lds128(part_a + (r & 31) * 4 + 16);
+                    v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w;
+                    v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
                 }
             }
-        } else if (r >= 0) {
+        } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) dst[k] = 0.0f;
+            for (int k = 0; k < 8; ++k) v[k] = 0.0f;
         }
-        if (r >= 0 && (r & 31) == 24) {
-            const uint32_t base = (uint32_t)r - 24u;
-            __syncthreads();
-            // rows w, w+NW, ...: sum the formant groups in index order (Array::sum, :123), scale (:574)
-            for (int row = w; row < 32; row += NW) {
-                const uint32_t rl = row_len[row];
-                if (base + lane < rl) {
-                    float acc = 0.0f;
+        if (r >= 0) {
+            sts128(part_a + (r & 31) * 4, v[0], v[1], v[2], v[3]);
+            sts128(part_a + (r & 31) * 4 + 16, v[4], v[5], v[6], v[7]);
+            if ((r & 31) == 24) {
+                const uint32_t base = (uint32_t)r - 24u;
+                __syncthreads();
+                // 8 lanes per row, 4 rows per pass: sum the formant groups in index order (Array::sum, :123),
+                // scale (:574), store 16 bytes per lane = 128 contiguous bytes per row
+                const int sub = lane >> 3, l8 = lane & 7;
+#pragma unroll 1
+                for (int row = w * 4 + sub; row < 32; row += NW * 4) {
+                    const uint32_t rl = row_len[row];
+                    const uint32_t s0 = base + l8 * 4;
+                    if (s0 < rl) {
+                        float4 acc = *reinterpret_cast<const float4*>(&part[0][row][l8 * 4]);
 #pragma unroll
-                    for (int f = 0; f < NW; ++f) acc += part[f][row][lane];
-                    acc *= 0.5f;
-                    const unsigned long long o = row_out[row] + base + lane;
-                    if (format == GRAIL_F32) {
-                        reinterpret_cast<float*>(out)[o] = acc;
-                    } else {
-                        // (x * i16::MAX as f32) as i16: truncating, saturating, NaN -> 0 (examples/cli.rs:50)
-                        const float sc = acc * 32767.0f;
-                        const int q = (sc != sc) ? 0 : __float2int_rz(fminf(fmaxf(sc, -32768.0f), 32767.0f));
-                        reinterpret_cast<short*>(out)[o] = (short)q;
+                        for (int f = 1; f < NW; ++f) {
+                            const float4 t = *reinterpret_cast<const float4*>(&part[f][row][l8 * 4]);
+                            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+                        }
+                        acc.x *= 0.5f; acc.y *= 0.5f; acc.z *= 0.5f; acc.w *= 0.5f;
+                        const unsigned long long o = row_out[row] + s0;
+                        const uint32_t cnt = min(4u, rl - s0);
+                        if (format == GRAIL_F32) {
+                            float* op = reinterpret_cast<float*>(out) + o;
+                            if (cnt == 4 && (o & 3ull) == 0) {
+                                *reinterpret_cast<float4*>(op) = acc;
+                            } else {
+                                const float a4[4] = { acc.x, acc.y, acc.z, acc.w };
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    if ((uint32_t)q < cnt) op[q] = a4[q];
+                            }
+                        } else {
+                            // (x * i16::MAX as f32) as i16: truncating, saturating, NaN -> 0 (examples/cli.rs:50)
+                            short* op = reinterpret_cast<short*>(out) + o;
+                            const float a4[4] = { acc.x, acc.y, acc.z, acc.w };
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float sc = a4[q] * 32767.0f;
+                                const int qi = (sc != sc) ? 0 : __float2int_rz(fminf(fmaxf(sc, -32768.0f), 32767.0f));
+                                if ((uint32_t)q < cnt) op[q] = (short)qi;
+                            }
+                        }
                     }
                 }
+                __syncthreads();
             }
-            __syncthreads();
         }
     }
 }
