@@ -611,8 +611,8 @@ struct FormantLane {
     int fi;                 // formant index, -1 if this slot is unused
 };
 
-template <int FPT> struct FormantCfg { static constexpr int warps_per_sm = 32; };   // 64 registers per lane
-template <> struct FormantCfg<2> { static constexpr int warps_per_sm = 20; };       // ~100 registers per lane
+template <int FPT> struct FormantCfg { static constexpr int warps_per_sm = 24; };   // 80 registers per lane
+template <> struct FormantCfg<2> { static constexpr int warps_per_sm = 16; };       // 128 registers per lane
 
 template <int NW, int FPT>
 __global__ void __launch_bounds__(NW * 32, FormantCfg<FPT>::warps_per_sm / NW)
@@ -646,7 +646,7 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
     const float jinc = U.voice.jitter_frequency;
     const float dff = U.voice.jitter_delta_formant_frequency;
     const float hda = 0.5f * U.voice.jitter_delta_amplitude;   // :769
-    const float quiet_t = 9.0f * dt;
+    const float quiet_t = 9.0f * dt, quiet_j = 1.0f - 9.0f * jinc;
     const uint32_t jseed = U.voice.jitter_seed;
 
     FormantLane L[FPT];
@@ -731,46 +731,58 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
         load_segment();
     }
 
-    // one sample: all formants of this lane; returns their v1 sum (band-pass outputs, :566)
-    auto sample = [&](float saw) -> float {
-        const float alpha = fminf(time * inv_bl, 1.0f);                      // :899
-        s_noise = s_noise * LCG_A + LCG_C;                                   // :40
+    // Per-sample coefficients of one formant at clock values (alpha, jph): the Sequencer blend (:404-414), the
+    // Jitter perturbation (:764-773), exp_approx (:75-82) and the SVF coefficients (:555-562).
+    struct Coef { float a1, a2, a3, lp, amp, br, tb; };   // lp = 1 - exp_approx(smooth)
+    auto coeffs = [&](const FormantLane& F, float alpha, float jp) -> Coef {
+        Coef c;
+        const float ff = fmaf(jp, F.ff2, fmaf(alpha, F.ff1, F.ff0));
+        const float bw = fmaf(alpha, F.bw1, F.bw0);
+        const float o = fmaf(alpha, F.om1, F.om0);                            // 1 - smooth
+        c.br = fmaf(alpha, F.br1, F.br0);
+        c.tb = fmaf(alpha, F.tb1, F.tb0);
+        c.amp = fmaf(alpha, F.am1, F.am0) * fmaf(jp, F.aj1, F.aj0);
+        const float o2 = o * o;
+        c.lp = fmaf(-o2 * o2, o, 1.0f);
+        float num, den;
+        tan_nd(ff, &num, &den);
+        const float g = num * frcp(den);
+        const float kq = bw * frcp(ff);
+        c.a1 = frcp(fmaf(g, g + kq, 1.0f));
+        c.a2 = g * c.a1;
+        c.a3 = g * c.a2;
+        return c;
+    };
+    // One filter step of one formant (:531-571): breath mix, one-pole low-pass, turbulence, amplitude, SVF tick.
+    auto tick = [&](FormantLane& F, const Coef& c, float saw, float d1, float nzm1) -> float {
+        const float nw = fmaf(c.br, d1, saw);                                 // :531
+        F.a = fmaf(c.lp, nw - F.a, F.a);                                      // :538
+        const float v0 = F.a * fmaf(c.tb, nzm1, 1.0f) * c.amp;                // :544-550
+        const float v3 = v0 - F.c;                                            // :565
+        const float v1 = fmaf(c.a1, F.b, c.a2 * v3);
+        const float v2 = fmaf(c.a3, v3, fmaf(c.a2, F.b, F.c));
+        F.b = fmaf(2.0f, v1, -F.b);
+        F.c = fmaf(2.0f, v2, -F.c);
+        return v1;
+    };
+    // aspiration noise of the next sample (:528) and the two differences every formant uses
+    auto noise = [&](float saw, float& d1, float& nzm1) {
+        s_noise = s_noise * LCG_A + LCG_C;                                    // :40
         const float nz = fmaf(__uint_as_float((s_noise >> 9) | 0x3F800000u), 2.0f, -3.0f);
-        const float d1 = nz - saw, nzm1 = nz - 1.0f;
+        d1 = nz - saw;
+        nzm1 = nz - 1.0f;
+    };
+    // one sample with exact per-sample coefficients: all formants of this lane; returns their v1 sum (:566)
+    auto sample = [&](float saw) -> float {
+        const float alpha = fminf(time * inv_bl, 1.0f);                       // :899
+        float d1, nzm1;
+        noise(saw, d1, nzm1);
         float acc = 0.0f;
 #pragma unroll
-        for (int j = 0; j < FPT; ++j) {
-            FormantLane& F = L[j];
-            const float ff = fmaf(jph, F.ff2, fmaf(alpha, F.ff1, F.ff0));
-            const float bw = fmaf(alpha, F.bw1, F.bw0);
-            const float o = fmaf(alpha, F.om1, F.om0);                        // 1 - smooth
-            const float br = fmaf(alpha, F.br1, F.br0);
-            const float tb = fmaf(alpha, F.tb1, F.tb0);
-            const float amp = fmaf(alpha, F.am1, F.am0) * fmaf(jph, F.aj1, F.aj0);
-            // source: breath mix, one-pole low-pass, turbulence, amplitude (:531-550)
-            const float nw = fmaf(br, d1, saw);
-            const float o2 = o * o;
-            const float a5 = o2 * o2 * o;                                     // exp_approx :75-82
-            F.a = fmaf(1.0f - a5, nw - F.a, F.a);                             // :538
-            const float v0 = F.a * fmaf(tb, nzm1, 1.0f) * amp;                // :544-550
-            // SVF coefficients (:555-562)
-            float num, den;
-            tan_nd(ff, &num, &den);
-            const float g = num * frcp(den);
-            const float kq = bw * frcp(ff);
-            const float a1 = frcp(fmaf(g, g + kq, 1.0f));
-            const float a2 = g * a1;
-            const float a3 = g * a2;
-            // SVF tick (:565-571)
-            const float v3 = v0 - F.c;
-            const float v1 = fmaf(a1, F.b, a2 * v3);
-            const float v2 = fmaf(a3, v3, fmaf(a2, F.b, F.c));
-            F.b = fmaf(2.0f, v1, -F.b);
-            F.c = fmaf(2.0f, v2, -F.c);
-            acc += v1;
-        }
+        for (int j = 0; j < FPT; ++j) acc += tick(L[j], coeffs(L[j], alpha, jph), saw, d1, nzm1);
         return acc;
     };
+
     // value-noise wrap: current <- next, draw the new next, refold  (:294-301).  Small, so it is inlined after
     // every sample of the unrolled block; lanes hit it at different samples (one lane in ~2756 per sample).
     auto jitter_wrap = [&]() {
@@ -829,16 +841,73 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
     if (-(int)wmax >= r_lo && -(int)wmax < r_hi) fetch();
     const unsigned part_a = (unsigned)__cvta_generic_to_shared(&part[w][lane][0]);
 
+    Coef cend[FPT];        // coefficients at the current clock values (the next block's start point)
+    bool c_valid = false;
+#pragma unroll
+    for (int j = 0; j < FPT; ++j) cend[j] = Coef{ 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+
     // ---- one loop over [-wmax, lmax) in steps of 8: warm-up (r < 0, no output) then the chunk itself
     for (int r = -(int)wmax; r < (int)lmax; r += 8) {
         const bool act = r >= r_lo && r < r_hi;
         const float4 sa = na, sb = nb;
         if (r + 8 >= r_lo && r + 8 < r_hi) fetch();
         float v[8];
+        // Block classes.  hand: a phoneme hand-over may fall inside (per lane, rare: generic per-sample loop).
+        // exact: a value-noise wrap or the alpha clip falls inside, so the parameters have a kink in this block; if
+        // ANY lane of the warp is in that class the whole warp takes the exact per-sample path (a uniform branch).
+        // Otherwise every parameter is linear in time over the block and the 7 per-sample coefficients are
+        // interpolated between the block's end points (error ~ h^2/8 c'' ~ 1e-9 relative, far below f32 rounding),
+        // which removes the blend / tan_approx / reciprocal work from 7 of every 8 samples.
+        const bool hand = act && !(time > quiet_t);
+        const float a_now = time * inv_bl, a_end = fmaf(8.0f, ndt, time) * inv_bl;
+        const bool kink = act && !hand && (!(jph < quiet_j) || ((a_now > 1.0f) != (a_end > 1.0f)));
+        const bool warp_exact = __any_sync(0xffffffffu, kink);
         if (act) {
-            if (time > quiet_t) {
-                // no hand-over can fall inside these 8 samples: literal clocks, one inlined wrap test per sample
+            if (!hand && !warp_exact) {
                 const float s8[8] = { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w };
+                Coef c0[FPT], dc[FPT];
+                if (!c_valid) {
+                    const float alpha = fminf(time * inv_bl, 1.0f);
+#pragma unroll
+                    for (int j = 0; j < FPT; ++j) cend[j] = coeffs(L[j], alpha, jph);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {       // the clocks stay literal f32 chains  (:861, :291)
+                    time = __fadd_rn(time, ndt);
+                    jph = __fadd_rn(jph, jinc);
+                }
+                {
+                    const float alpha = fminf(time * inv_bl, 1.0f);
+#pragma unroll
+                    for (int j = 0; j < FPT; ++j) {
+                        c0[j] = cend[j];
+                        cend[j] = coeffs(L[j], alpha, jph);
+                        dc[j].a1 = cend[j].a1 - c0[j].a1; dc[j].a2 = cend[j].a2 - c0[j].a2; dc[j].a3 = cend[j].a3 - c0[j].a3;
+                        dc[j].lp = cend[j].lp - c0[j].lp; dc[j].amp = cend[j].amp - c0[j].amp;
+                        dc[j].br = cend[j].br - c0[j].br; dc[j].tb = cend[j].tb - c0[j].tb;
+                    }
+                }
+                c_valid = true;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float d1, nzm1;
+                    noise(s8[k], d1, nzm1);
+                    const float t = (float)k * 0.125f;
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < FPT; ++j) {
+                        Coef c;
+                        c.a1 = fmaf(dc[j].a1, t, c0[j].a1); c.a2 = fmaf(dc[j].a2, t, c0[j].a2); c.a3 = fmaf(dc[j].a3, t, c0[j].a3);
+                        c.lp = fmaf(dc[j].lp, t, c0[j].lp); c.amp = fmaf(dc[j].amp, t, c0[j].amp);
+                        c.br = fmaf(dc[j].br, t, c0[j].br); c.tb = fmaf(dc[j].tb, t, c0[j].tb);
+                        acc += tick(L[j], c, s8[k], d1, nzm1);
+                    }
+                    v[k] = acc;
+                }
+            } else if (!hand) {
+                // a kink somewhere in the warp: exact coefficients every sample, one inlined wrap test per sample
+                const float s8[8] = { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w };
+                c_valid = false;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     v[k] = sample(s8[k]);
@@ -848,6 +917,7 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
                 }
             } else {
                 // the phoneme's last samples: generic per-sample loop (results parked in the smem row)
+                c_valid = false;
 #pragma unroll 1
                 for (int k = 0; k < 8; ++k) {
                     const float4 q = k < 4 ? sa : sb;
