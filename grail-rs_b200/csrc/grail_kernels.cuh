@@ -147,7 +147,7 @@ __device__ __forceinline__ FreqSeg load_freq_seg(const float* ue, uint32_t p, ui
 // closed form at the run start, then replayed literally; the scalar frequency path uses strict ops in
 // the reference's order (blend :406, value-noise lerp :254, jitter add :763).
 // ------------------------------------------------------------------------------------------------
-constexpr int FREQ_RUN = 128;
+constexpr int FREQ_RUN = 512;   // samples per lane: amortises the two closed-form clock fast-forwards
 
 __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_item)
 {
@@ -200,6 +200,10 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
         return fr;
     };
     for (uint32_t k0 = 0; k0 < count; k0 += 8) {
+        if (k0 != 0 && (k0 & 127u) == 0) {   // one flag word per 128 samples (f_off, n0 and the run start are 128-aligned)
+            P.fflags[(U.f_off + ns + k0 - 128) >> 7] = odd ? 1u : 0u;
+            odd = false;
+        }
         const bool quiet = (k0 + 8 <= count) && (time > 9.0f * dt) && (jph + 9.0f * jinc < 1.0f);
         if (quiet) { // no hand-over and no wrap inside these 8 samples: literal clocks, no event tests
             float buf[8];
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
             }
         }
     }
-    P.fflags[(U.f_off + ns) >> 7] = odd ? 1u : 0u;   // runs are 128-aligned (CL and f_off are multiples of 256)
+    P.fflags[(U.f_off + ns + ((count - 1) & ~127u)) >> 7] = odd ? 1u : 0u;   // the last (possibly partial) 128-block
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -339,13 +343,26 @@ __device__ __forceinline__ float phase_steps8(float phase, const float4& fa, con
     return phase;
 }
 
-// one 32-sample quad that contains a carrier wrap, redone 8 samples at a time (rare: kept out of line so the
-// chain warp's straight-line code stays small); f_a / p_a are shared-window addresses of the quad's F_t and
-// of its four block-start phase slots
-__device__ __noinline__ float phase_redo_quad(float phase, unsigned f_a, unsigned p_a, bool lane0)
+// One 32-sample quad whose speculative chain reached 1.0: a carrier wrap lies inside (rare: kept out of line so
+// the chain warp's straight-line code stays small).  The speculative values are exact up to the wrap, so the
+// 8-sample blocks before the first block whose END value reached 1.0 keep their start phases; that block is
+// stepped exactly as the reference does, and the blocks after it are chained again from the corrected phase.
+// ps[b] = speculative phase at the start of block b, ps[4] = at the end of the quad.
+__device__ __noinline__ float phase_redo_quad(float ps0, float ps1, float ps2, float ps3, float ps4, unsigned f_a,
+                                              unsigned p_a, bool lane0)
 {
+    const float pe[5] = { ps0, ps1, ps2, ps3, ps4 };
+    int b = 0;
+#pragma unroll
+    for (int i = 1; i <= 3; ++i) b += (pe[i] < 1.0f) ? 1 : 0;     // monotone: number of leading blocks that end below 1.0
+    float phase = b == 0 ? ps0 : (b == 1 ? ps1 : (b == 2 ? ps2 : ps3));
+    if (lane0) sts128(p_a, ps0, ps1, ps2, ps3);                   // entries past b are overwritten below
+    {
+        const float4 fa = lds128(f_a + b * 32), fb = lds128(f_a + b * 32 + 16);
+        phase = phase_steps8(phase, fa, fb, 8);
+    }
 #pragma unroll 1
-    for (uint32_t b = 0; b < 4; ++b) {
+    for (++b; b < 4; ++b) {
         const float4 fa = lds128(f_a + b * 32), fb = lds128(f_a + b * 32 + 16);
         if (lane0) sts32(p_a + b * 4, phase);
         const float p4 = sadd(sadd(sadd(sadd(phase, fa.x), fa.y), fa.z), fa.w);
@@ -439,7 +456,7 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
                     }
                     if (lane0) sts128(pa_ + q * 16, ps[0], ps[1], ps[2], ps[3]);
                     if (__builtin_expect(p < 1.0f, 1)) phase = p;
-                    else phase = phase_redo_quad(phase, fa_ + q * 128, pa_ + q * 16, lane0);
+                    else phase = phase_redo_quad(ps[0], ps[1], ps[2], ps[3], p, fa_ + q * 128, pa_ + q * 16, lane0);
                 }
             }
             __syncwarp();
