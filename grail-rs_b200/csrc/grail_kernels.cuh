@@ -258,9 +258,8 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
 // already on the next tile.  Producer and consumer meet on mbarriers (full / empty per buffer).
 constexpr int PH_TILE = 256, PH_STAGES = 8, PH_AHEAD = 6, PH_UTTS = 4;
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+__device__ __forceinline__ void cp_async16(unsigned sa, const void* gmem)
 {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -272,14 +271,12 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
     const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+__device__ __forceinline__ void mbar_arrive(unsigned a)
 {
-    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile("{ .reg .b64 t; mbarrier.arrive.shared::cta.b64 t, [%0]; }" ::"r"(a) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+__device__ __forceinline__ void mbar_wait(unsigned a, unsigned parity)
 {
-    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -392,6 +389,8 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
     const uint32_t n = U.n_samples;
     if (n == 0) return;
     const uint32_t ntiles = (n + PH_TILE - 1) / PH_TILE;
+    const unsigned full_a = (unsigned)__cvta_generic_to_shared(&s_full[slot][0]);     // + 8 * buf
+    const unsigned empty_a = (unsigned)__cvta_generic_to_shared(&s_empty[slot][0]);
 
     if (is_chain) {
         // ---------------- chain warp ----------------
@@ -404,10 +403,10 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
         auto issue = [&](uint32_t tile) {
             if (tile < ntiles) {
                 const uint32_t off = tile * PH_TILE + lane * 8;
-                float* dst = &sF[slot][tile % PH_STAGES][lane * 8];
+                const unsigned dst = sF_a + ((tile % PH_STAGES) * PH_TILE + lane * 8) * 4;
                 if (off < npad) {
                     cp_async16(dst, src + off);
-                    cp_async16(dst + 4, src + off + 4);
+                    cp_async16(dst + 16, src + off + 4);
                 }
                 // the tile's two sign-flag words ride the same ring (the flag array is padded past the end)
                 if (lane == 0) cp_async8(sG_a + (tile % PH_STAGES) * 8, flags + 2 * tile);
@@ -422,7 +421,7 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
             issue(tile + PH_AHEAD);             // stage (tile-2) % 8: released by the saw warp two tiles ago
             cp_async_wait<PH_AHEAD>();
             __syncwarp();
-            mbar_wait(&s_empty[slot][buf], ((tile >> 1) & 1) ^ 1);   // first use of each buffer passes at once
+            mbar_wait(empty_a + buf * 8, ((tile >> 1) & 1) ^ 1);   // first use of each buffer passes at once
             const unsigned fa_ = sF_a + (tile % PH_STAGES) * (PH_TILE * 4);   // this tile's F_t
             const unsigned pa_ = sP_a + buf * (32 * 4);                        // block-start phases out
             const uint32_t odd = lds32u(sG_a + (tile % PH_STAGES) * 8) | lds32u(sG_a + (tile % PH_STAGES) * 8 + 4);
@@ -442,11 +441,16 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
                 // pays ~20 cycles for every taken branch, so there is no loop here and the only branch (the rare
                 // redo) is forward.  Increments are non-negative (k_frequency's tile flag), so the chain is
                 // monotone and its last value bounds the rest: p32 < 1 proves no wrap happened.
+                float4 fv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) fv[i] = lds128(fa_ + i * 16);
 #pragma unroll
                 for (uint32_t q = 0; q < 8; ++q) {
-                    float4 fv[8];
+                    float4 fn[8];                       // next quad's increments, loaded in the shadow of this chain
+                    if (q < 7) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) fv[i] = lds128(fa_ + q * 128 + i * 16);
+                        for (int i = 0; i < 8; ++i) fn[i] = lds128(fa_ + (q + 1) * 128 + i * 16);
+                    }
                     float p = phase;
                     float ps[4];
 #pragma unroll
@@ -457,10 +461,14 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
                     if (lane0) sts128(pa_ + q * 16, ps[0], ps[1], ps[2], ps[3]);
                     if (__builtin_expect(p < 1.0f, 1)) phase = p;
                     else phase = phase_redo_quad(ps[0], ps[1], ps[2], ps[3], p, fa_ + q * 128, pa_ + q * 16, lane0);
+                    if (q < 7) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) fv[i] = fn[i];
+                    }
                 }
             }
             __syncwarp();
-            if (lane0) mbar_arrive(&s_full[slot][buf]);   // release: the tile's phases (and its F stage) are ready
+            if (lane0) mbar_arrive(full_a + buf * 8);   // release: the tile's phases (and its F stage) are ready
         }
     } else {
         // ---------------- saw warp ----------------
@@ -468,7 +476,7 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
         const uint32_t CL = P.chunk_len;
         for (uint32_t tile = 0; tile < ntiles; ++tile) {
             const int buf = tile & 1;
-            mbar_wait(&s_full[slot][buf], (tile >> 1) & 1);
+            mbar_wait(full_a + buf * 8, (tile >> 1) & 1);
             const float* f = sF[slot][tile % PH_STAGES];
             const uint32_t b0 = tile * PH_TILE + lane * 8;
             float4 fa, fb;
@@ -479,7 +487,7 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
                 p = sP[slot][buf][lane];
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[slot][buf]);   // both shared tiles are in registers now
+            if (lane == 0) mbar_arrive(empty_a + buf * 8);   // both shared tiles are in registers now
             if (b0 < n) {
                 const float fv[8] = { fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w };
                 const uint32_t valid = min(8u, n - b0);

@@ -1,0 +1,73 @@
+"""BASELINE.json configs 3, 4 and 5 on the GPU at (or near) full size: exact counts, bit-exact F_t / phase taps where
+the oracle finishes in seconds, spot-checked audio parity, and size-independent properties."""
+import numpy as np
+import pytest
+
+import grail_rs_b200 as g
+from grail_rs_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+MAX_ABS, MIN_SNR_DB = 1e-4, 90.0     # north_star tolerance
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = g.Context(0)
+    yield c
+    c.close()
+
+
+def test_config3_long_form(ctx, oracle):
+    """one 10-minute utterance: 26 457 161 samples, one chain, 1 200 phonemes"""
+    elems, offs, vp = W.config3(1200)
+    plan = ctx.plan(elems, offs, vp)
+    assert plan.total_samples == 26457161
+    plan.launch()
+    out = plan.read_output()
+    print(plan.timings())
+    f, ph, saw = plan.read_intermediates()
+    want, tr, fin = oracle.synthesize(elems, vp[0], trace=True)
+    assert np.array_equal(f.view(np.uint32), tr["frequency"].view(np.uint32))          # bit-exact fundamental
+    assert np.array_equal(ph.view(np.uint32), tr["carrier_phase"].view(np.uint32))     # bit-exact carrier phase
+    st = W.parity_stats(out, want)
+    print(st)
+    assert st["max_abs"] <= MAX_ABS and st["snr_db"] >= MIN_SNR_DB, st
+    plan.close()
+
+
+def test_config4_random_voices_sharded_shape(ctx, oracle):
+    """short utterances with per-utterance random voices (8 active formants, no time chunking needed);
+    4 096 of the 65 536, the slice one of 16 ranks would own"""
+    elems, offs, vp = W.config4(4096, first_utt=8192)
+    plan = ctx.plan(elems, offs, vp)
+    counts = g.count_samples(elems, offs, vp)
+    assert plan.total_samples == int(counts.sum())
+    plan.launch()
+    out = plan.read_output()
+    oo = plan.out_offsets
+    print(plan.timings(), plan.total_samples)
+    assert np.isfinite(out).all()
+    worst = {"max_abs": 0.0, "snr_db": 1e9}
+    for u in (0, 1, 2, 777, 2048, 4095):
+        want, _, _ = oracle.synthesize(elems[offs[u]:offs[u + 1]], vp[u])
+        st = W.parity_stats(out[oo[u]:oo[u + 1]], want)
+        assert st["max_abs"] <= MAX_ABS and st["snr_db"] >= MIN_SNR_DB, (u, st)
+        worst = {"max_abs": max(worst["max_abs"], st["max_abs"]), "snr_db": min(worst["snr_db"], st["snr_db"])}
+    print(worst)
+    plan.close()
+
+
+@pytest.mark.parametrize("rate,count", [(16000.0, 80003), (22050.0, 110244), (44100.0, 220476), (48000.0, 240016)])
+def test_config5_sample_rate_sweep(ctx, oracle, rate, count):
+    """config-2 shape at four sample rates (the Intonator 'lookahead' of the config name is a no-op in the reference)"""
+    elems, offs, vp = W.config2(64, 10, sample_rate=rate)
+    plan = ctx.plan(elems, offs, vp)
+    assert plan.total_samples == 64 * count
+    plan.launch()
+    out = plan.read_output()
+    oo = plan.out_offsets
+    for u in (0, 31, 63):
+        want, _, _ = oracle.synthesize(elems[offs[u]:offs[u + 1]], vp[u])
+        st = W.parity_stats(out[oo[u]:oo[u + 1]], want)
+        assert st["max_abs"] <= MAX_ABS and st["snr_db"] >= MIN_SNR_DB, (rate, u, st)
+    plan.close()
