@@ -37,6 +37,7 @@ struct UttDev {
     uint64_t f_off;                // first entry in the linear F_t scratch (multiple of 8)
     grail_voice_params voice;
     float    init_phase;           // carrier phase at sample 0 (0 for a fresh utterance)
+    int32_t  pscan;                // >= 0: index of this utterance's exact parallel phase scan (long utterances)
 };
 
 struct JitSchedDev {
@@ -65,6 +66,7 @@ struct PlanDev {
     float*              saw;       // tiled: [group][j/8][lane][8]
     float*              phase_dbg; // optional linear carrier phase tap (same indexing as F), may be null
     uint32_t*           fflags;    // one word per 128 F_t entries: nonzero if any is negative or NaN
+    const uint32_t*     pscan_status; // 16 words per parallel phase scan: {mismatches, done, rounds, unsupported, history[12]}
     uint32_t*           err;       // device error word
     uint32_t n_utts, n_items, n_groups, n_jscheds;
     uint32_t chunk_len;            // CL, multiple of 256
@@ -388,6 +390,7 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
     const UttDev& U = P.utts[u];
     const uint32_t n = U.n_samples;
     if (n == 0) return;
+    if (U.pscan >= 0 && P.pscan_status[16 * U.pscan + 1] != 0u) return;   // the exact parallel scan already did it
     const uint32_t ntiles = (n + PH_TILE - 1) / PH_TILE;
     const unsigned full_a = (unsigned)__cvta_generic_to_shared(&s_full[slot][0]);     // + 8 * buf
     const unsigned empty_a = (unsigned)__cvta_generic_to_shared(&s_empty[slot][0]);
@@ -517,6 +520,339 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 (parallel form, for long utterances): the exact carrier phase without the serial chain.
+//
+// f32 addition is "add exactly, then round to the grid of the result's binade", so in fixed point (units of
+// 2^-40 cycle; every phase and every F_t >= 2^-16 is an integer there) one step is
+//     P' = RHE(P + Fi, 2^g) mod 2^40,    g = max(0, msb(P + Fi) - 23)        (RHE = round half to even)
+// The only thing that keeps it from being a prefix sum is g (and the parity bit of an exact tie), which depend
+// on P itself -- but only weakly: an ESTIMATE of P that is off by a few ulps still classifies almost every
+// step correctly.  Fixed-point iteration:
+//   round 0   estimate P~ = exact prefix sum of Fi (no rounding at all)
+//   each round  classify every step from P~ (grid g, "wraps", tie parity); GIVEN those, the rounded increment of a
+//             step depends only on the low 17 bits L of P, and L restarts from 0 after every wrap -- so each
+//             wrap-to-wrap segment is replayed independently (one lane per 256-sample block replays the segments
+//             that start in it), giving the rounded increments; an exact integer prefix sum of them is the new P~
+//   stop      when a fully parallel check with REAL f32 ops, step(P_t, F_t) == P_{t+1} for every t, passes:
+//             by induction from P_0 the trajectory is then the reference's, bit for bit.
+// Converges in 3-5 rounds (measured); if it has not after PS_MAX_ROUNDS, or some F_t is outside [2^-16, 0.5],
+// the done flag stays 0 and k_phase_pair runs the serial chain for that utterance instead.
+// ------------------------------------------------------------------------------------------------
+constexpr int PS_MAX_ROUNDS = 12;
+constexpr int PS_BLOCK = 256;          // samples per replay lane
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr unsigned long long PS_ONE = 1ull << 40, PS_MASK = PS_ONE - 1ull;
+
+struct PScanDev {
+    const float* F;                 // the utterance's F_t
+    unsigned long long* P;          // n + 1 fixed-point phases (estimate, then result)
+    unsigned long long* inc;        // n rounded increments
+    unsigned long long* bsum;       // scan spine
+    unsigned char* sflag;           // per step: bit0 parity of the carry into the high part, bit1 tie on a wrap step, bit2 parity of c at the tie
+    unsigned char* bpar;            // per 256-step block: parity transducer (bit1 has_tie, bit0 xor), then incoming parity
+    uint32_t* status;               // {mismatches, done, rounds, unsupported}
+    uint32_t n;
+    unsigned long long p0;          // phase at sample 0
+};
+
+__device__ __forceinline__ unsigned long long ps_fix(float f) { return (unsigned long long)(f * 1099511627776.0f); } // * 2^40, exact
+__device__ __forceinline__ int ps_grid(unsigned long long x) { const int m = 63 - __clzll((long long)(x | 1ull)); return m > 23 ? m - 23 : 0; }
+// round x to a multiple of 2^g, half to even; `odd_hint` overrides the parity bit when it is not inside x
+__device__ __forceinline__ unsigned long long ps_rhe(unsigned long long x, int g, int parity_override /* -1: use x */)
+{
+    if (g == 0) return x;
+    const unsigned long long unit = 1ull << g, rem = x & (unit - 1ull), base = x - rem, half = unit >> 1;
+    const unsigned long long odd = parity_override < 0 ? ((base >> g) & 1ull) : (unsigned long long)parity_override;
+    return (rem > half || (rem == half && odd)) ? base + unit : base;
+}
+
+__global__ void k_ps_init(PScanDev S)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S.n) return;                        // (status words are zeroed by the host before this launch)
+    const float f = S.F[t];
+    if (!(f >= 1.52587890625e-05f && f <= 0.5f)) atomicOr(S.status + 3, 1u);   // outside [2^-16, 0.5]: not this path
+    S.inc[t] = ps_fix(f);
+}
+
+// exclusive prefix sum of inc (mod 2^64, which 2^40 divides) -> P[t] = (p0 + sum_{s<t} inc_s) mod 2^40, t = 0..n
+__global__ void __launch_bounds__(SCAN_THREADS) k_ps_scan_reduce(PScanDev S)
+{
+    if (S.status[1] | S.status[3]) return;
+    __shared__ unsigned long long sh[SCAN_THREADS / 32];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    unsigned long long s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+        if (base + i < S.n) s += S.inc[base + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long tot = 0;
+        for (int i = 0; i < SCAN_THREADS / 32; ++i) tot += sh[i];
+        S.bsum[blockIdx.x] = tot;
+    }
+}
+__global__ void __launch_bounds__(1024) k_ps_scan_spine(PScanDev S, uint32_t nb)
+{
+    if (S.status[1] | S.status[3]) return;
+    __shared__ unsigned long long sh[32];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < nb; b0 += 1024) {
+        const uint32_t i = b0 + threadIdx.x;
+        const unsigned long long v = i < nb ? S.bsum[i] : 0ull;
+        unsigned long long x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned long long w = sh[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long y = __shfl_up_sync(0xffffffffu, w, o);
+                if (threadIdx.x >= o) w += y;
+            }
+            sh[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const unsigned long long wprev = (threadIdx.x >> 5) ? sh[(threadIdx.x >> 5) - 1] : 0ull;
+        const unsigned long long incl = x + wprev + carry;
+        if (i < nb) S.bsum[i] = incl - v;            // exclusive
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = incl;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_ps_scan_apply(PScanDev S)
+{
+    if (S.status[1] | S.status[3]) return;
+    __shared__ unsigned long long sh[SCAN_THREADS / 32];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    unsigned long long v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = (base + i < S.n) ? S.inc[base + i] : 0ull;
+        s += v[i];
+    }
+    unsigned long long x = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = x;
+    __syncthreads();
+    unsigned long long woff = 0;
+    for (int i = 0; i < (int)(threadIdx.x >> 5); ++i) woff += sh[i];
+    unsigned long long run = S.p0 + S.bsum[blockIdx.x] + woff + (x - s);   // exclusive prefix of this lane's first item
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i <= S.n) S.P[base + i] = run & PS_MASK;                // P[n] (the final phase) included
+        run += v[i];
+    }
+}
+
+// One lane per 256-sample block.  The low bits L restart from 0 after every wrap, so the lane first looks BACK for
+// the last step before its block that wraps under the current estimate (a whole carrier period at most), replays
+// forward from there without writing, and then replays its own block writing the rounded increments and the
+// parity flags.  Grids, wraps and tie flags are classified from the estimate P~.
+constexpr uint32_t PS_MAX_LOOKBACK = 1u << 16;
+
+__global__ void __launch_bounds__(128) k_ps_replay(PScanDev S)
+{
+    if (S.status[1] | S.status[3]) return;
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t t0_ = (uint64_t)b * PS_BLOCK;
+    if (t0_ >= S.n) return;
+    const uint32_t t0 = (uint32_t)t0_;
+    const uint32_t t1 = (uint32_t)min((uint64_t)S.n, t0_ + PS_BLOCK);
+    // step s under the current estimate: exact-sum estimate x, its grid, and whether it reaches 1.0
+    auto classify = [&](uint32_t s, unsigned long long& fi, int& g) -> bool {
+        fi = ps_fix(__ldg(S.F + s));
+        const unsigned long long x = S.P[s] + fi;
+        g = ps_grid(x);
+        return ps_rhe(x, g, -1) >= PS_ONE;
+    };
+    // look back for the segment start
+    uint32_t s0 = t0;
+    {
+        uint32_t back = 0;
+        unsigned long long fi;
+        int g;
+        while (s0 > 0 && !classify(s0 - 1, fi, g)) {
+            --s0;
+            if (++back > PS_MAX_LOOKBACK) {          // a carrier slower than 0.7 Hz: leave it to the serial chain
+                atomicOr(S.status + 3, 1u);
+                return;
+            }
+        }
+    }
+    unsigned long long L = (s0 == 0) ? (S.p0 & 0x1FFFFull) : 0ull;
+    for (uint32_t s = s0; s < t1; ++s) {
+        unsigned long long fi;
+        int g;
+        const bool wraps = classify(s, fi, g);
+        // The low bits decide the rounding.  Only an exact tie on a wrap step (g == 17, low 17 bits == 2^16)
+        // needs a bit from above them: the parity of the high part.  Those steps are rounded DOWN here and
+        // flagged; k_ps_parity_* resolves them with an exact parity scan (common when the pitch is 0.25).
+        const unsigned long long xl = L + fi;
+        const bool tie = (g == 17) && ((xl & 0x1FFFFull) == 0x10000ull);
+        const unsigned long long r = tie ? (xl & ~0x1FFFFull) : ps_rhe(xl, g, -1);
+        if (s >= t0) {
+            S.inc[s] = r - L;
+            S.sflag[s] = tie ? (unsigned char)(2u | (((xl >> 17) & 1ull) << 2)) : (unsigned char)((r >> 17) & 1ull);
+        }
+        L = wraps ? 0ull : (r & 0x1FFFFull);         // after a wrap the phase is a multiple of 2^-23: no low bits
+    }
+}
+
+// Parity of the high part Q = floor(P / 2^17) along the whole utterance.  A non-tie step adds a known carry
+// (parity bit0 of its flag); a tie step rounds to even, so Q is even after it whatever came before: per block the
+// parity map is either p -> p ^ x or the constant x, which composes associatively (a scan over blocks).
+__global__ void __launch_bounds__(128) k_ps_parity_block(PScanDev S)
+{
+    if (S.status[1] | S.status[3]) return;
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t t0 = (uint64_t)b * PS_BLOCK;
+    if (t0 >= S.n) return;
+    const uint32_t t1 = (uint32_t)min((uint64_t)S.n, t0 + PS_BLOCK);
+    unsigned x = 0, has_tie = 0;
+    for (uint32_t t = (uint32_t)t0; t < t1; ++t) {
+        const unsigned f = S.sflag[t];
+        if (f & 2u) { has_tie = 1; x = 0; } else x ^= f & 1u;
+    }
+    S.bpar[b] = (unsigned char)((has_tie << 1) | x);
+}
+// exclusive scan of the block transducers -> incoming parity of every block (one CTA walks the spine)
+__global__ void __launch_bounds__(1024) k_ps_parity_spine(PScanDev S, uint32_t nblk)
+{
+    if (S.status[1] | S.status[3]) return;
+    __shared__ unsigned sh[32];
+    __shared__ unsigned carry;                       // parity entering the current stripe
+    if (threadIdx.x == 0) carry = (unsigned)((S.p0 >> 17) & 1ull);
+    __syncthreads();
+    auto compose = [](unsigned a, unsigned b) -> unsigned { return (b & 2u) ? b : ((a & 2u) | ((a ^ b) & 1u)); };   // a then b
+    for (uint32_t b0 = 0; b0 < nblk; b0 += 1024) {
+        const uint32_t i = b0 + threadIdx.x;
+        const unsigned v = i < nblk ? (unsigned)S.bpar[i] : 0u;
+        unsigned x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x = compose(y, x);
+        }
+        if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned w = sh[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned y = __shfl_up_sync(0xffffffffu, w, o);
+                if (threadIdx.x >= o) w = compose(y, w);
+            }
+            sh[threadIdx.x] = w;
+        }
+        __syncthreads();
+        // inclusive map from the stripe start to the end of this block, then apply it to the stripe's incoming parity
+        unsigned incl = x;
+        if (threadIdx.x >> 5) incl = compose(sh[(threadIdx.x >> 5) - 1], x);
+        // exclusive: the map up to (not including) this block = shifted inclusive
+        const unsigned prev = __shfl_up_sync(0xffffffffu, incl, 1);
+        unsigned excl;
+        if ((threadIdx.x & 31) == 0) excl = (threadIdx.x >> 5) ? sh[(threadIdx.x >> 5) - 1] : 0u;   // identity = (no tie, xor 0)
+        else excl = prev;
+        const unsigned pin = (excl & 2u) ? (excl & 1u) : ((carry ^ excl) & 1u);
+        const unsigned pout = (incl & 2u) ? (incl & 1u) : ((carry ^ incl) & 1u);
+        __syncthreads();
+        if (i < nblk) S.bpar[i] = (unsigned char)pin;
+        if (threadIdx.x == 1023) carry = pout;
+        __syncthreads();
+    }
+}
+// second walk with the incoming parity known: round every flagged tie to even
+__global__ void __launch_bounds__(128) k_ps_parity_fix(PScanDev S)
+{
+    if (S.status[1] | S.status[3]) return;
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t t0 = (uint64_t)b * PS_BLOCK;
+    if (t0 >= S.n) return;
+    const uint32_t t1 = (uint32_t)min((uint64_t)S.n, t0 + PS_BLOCK);
+    unsigned p = S.bpar[b] & 1u;
+    for (uint32_t t = (uint32_t)t0; t < t1; ++t) {
+        const unsigned f = S.sflag[t];
+        if (f & 2u) {
+            if (((p ^ (f >> 2)) & 1u) != 0u) S.inc[t] += 0x20000ull;   // (Q + c) odd: round half UP to the even multiple
+            p = 0;
+        } else {
+            p ^= f & 1u;
+        }
+    }
+}
+
+// fully parallel proof: every step, redone with real f32 operations, must land on the next phase
+__global__ void k_ps_verify(PScanDev S)
+{
+    if (S.status[1] | S.status[3]) return;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false;
+    if (t < S.n) {
+        const unsigned long long p = S.P[t], q = S.P[t + 1];
+        const float a = __ull2float_rn(p) * 9.094947017729282e-13f;       // * 2^-40
+        const float c = __ull2float_rn(q) * 9.094947017729282e-13f;
+        bad = ((unsigned long long)(a * 1099511627776.0f) != p) || ((unsigned long long)(c * 1099511627776.0f) != q);
+        float nx = sadd(a, S.F[t]);                                       // :520
+        if (nx >= 1.0f) nx = ssub(nx, 1.0f);                              // :523-525
+        bad |= __float_as_uint(nx) != __float_as_uint(c);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(S.status, (unsigned)__popc(m));
+}
+__global__ void k_ps_check(PScanDev S)
+{
+    if (S.status[1] | S.status[3]) return;
+    if (S.status[2] < 12u) S.status[4 + S.status[2]] = S.status[0];   // mismatch history (diagnostics)
+    S.status[2] += 1;
+    if (S.status[0] == 0) S.status[1] = 1;      // converged: exact
+    S.status[0] = 0;
+}
+
+// phases -> polyBLEP saw in the tiled layout k_formant reads (same arithmetic as k_phase_pair's saw warp)
+__global__ void k_ps_saw(PScanDev S, PlanDev P, uint32_t utt)
+{
+    if (!S.status[1]) return;                   // not converged: k_phase_pair does this utterance
+    const uint32_t blk = blockIdx.x * blockDim.x + threadIdx.x;   // 8 samples per lane
+    const uint64_t b0 = (uint64_t)blk * 8;
+    if (b0 >= S.n) return;
+    const UttDev& U = P.utts[utt];
+    const uint32_t valid = (uint32_t)min((uint64_t)8, S.n - b0);
+    float s[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        s[k] = 0.0f;
+        if ((uint32_t)k < valid) {
+            const float ph = __ull2float_rn(S.P[b0 + k]) * 9.094947017729282e-13f;
+            const float f = S.F[b0 + k];
+            s[k] = ssub(smul(2.0f, ph), 1.0f);
+            if (!((ph >= f) && (ph <= ssub(1.0f, f)))) s[k] = saw_edge(ph, f);
+            if (P.phase_dbg) P.phase_dbg[U.f_off + b0 + k] = ph;
+        }
+    }
+    const uint32_t CL = P.chunk_len;
+    const uint32_t item = U.item_first + (uint32_t)(b0 / CL), j = (uint32_t)(b0 % CL);
+    float4* dst = reinterpret_cast<float4*>(P.saw + saw_index(item, j, CL));
+    dst[0] = make_float4(s[0], s[1], s[2], s[3]);
+    dst[1] = make_float4(s[4], s[5], s[6], s[7]);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -40,6 +40,7 @@ struct grail_ctx {
     uint32_t min_chunk = 2048;
     uint32_t max_chunk = 1u << 22;
     int      debug_taps = 0;
+    uint32_t pscan_min = 1u << 20;   // utterances at least this long get the exact parallel phase scan
     int      zero_copy_out = 0;      // 1: k_formant stores straight into pinned host output (measured slower: 23 vs 50 GB/s over PCIe)
     int      formants_per_lane = 2;  // 1 or 2 formants of an utterance share one lane's clocks, noise and saw
     // pinned staging for pageable D2H
@@ -131,6 +132,10 @@ struct grail_plan {
     void* d_out = nullptr; size_t d_out_bytes = 0; int d_out_format = -1;
     cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
     bool launched = false;
+    std::vector<PScanDev> pscans;          // exact parallel phase scans (one per long utterance)
+    std::vector<uint32_t> pscan_utt;
+    uint32_t* d_pscan_status = nullptr;
+    std::vector<void*> pscan_bufs;
     bool jit_on_host = false;   // few distinct jitter increments: schedules computed by the planner
     std::vector<JitRec> jrecs;
     uint32_t last_launches = 0;
@@ -277,6 +282,7 @@ static PlanDev plan_dev(const grail_plan* pl, bool with_dbg)
     P.phase_dbg = with_dbg ? pl->d_phase_dbg : nullptr;
     P.err = pl->d_err;
     P.fflags = pl->d_fflags;
+    P.pscan_status = pl->d_pscan_status;
     P.n_utts = pl->n_utts; P.n_items = pl->n_items; P.n_groups = pl->n_groups; P.n_jscheds = pl->n_jscheds;
     P.chunk_len = pl->chunk_len;
     P.warmup_nepers = (float)pl->ctx->warmup_nepers;
@@ -290,6 +296,8 @@ static void plan_release(grail_plan* pl)
     void* bufs[] = { pl->d_elems, pl->d_segs, pl->d_utts, pl->d_items, pl->d_jscheds, pl->d_jrecs, pl->d_F, pl->d_saw,
                      pl->d_phase_dbg, pl->d_err, pl->d_out, pl->d_fflags };
     for (void* b : bufs) pool_free(ctx, b);
+    for (void* b : pl->pscan_bufs) pool_free(ctx, b);
+    pool_free(ctx, pl->d_pscan_status);
     for (auto& e : pl->ev)
         if (e) cudaEventDestroy(e);
     delete pl;
@@ -332,6 +340,7 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
         U.n_samples = (uint32_t)n;
         U.voice = voices[u];
         U.init_phase = 0.0f;
+        U.pscan = -1;
         U.out_off = total;
         U.f_off = f_words;
         total += (uint64_t)n;
@@ -439,6 +448,20 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
     pl->n_groups = (pl->n_items + 31) / 32;
     pl->saw_words = (uint64_t)pl->n_groups * 32ull * pl->chunk_len;
 
+    // ---- long utterances: exact parallel phase scan instead of the serial chain (a handful at most; with many
+    //      long utterances the chains of k_phase_pair already run concurrently)
+    {
+        std::vector<uint32_t> longs;
+        for (uint32_t u = 0; u < n_utts; ++u)
+            if (pl->utts[u].n_samples >= ctx->pscan_min) longs.push_back(u);
+        if (!longs.empty() && longs.size() <= 16) {
+            for (uint32_t u : longs) {
+                pl->utts[u].pscan = (int32_t)pl->pscan_utt.size();
+                pl->pscan_utt.push_back(u);
+            }
+        }
+    }
+
     // ---- device buffers
     auto fail = [&](int code) { plan_release(pl); return code; };
 #define PA(ptr, bytes)                                                         \
@@ -466,6 +489,27 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
     PA(pl->d_fflags, (pl->f_words / 128 + 2) * sizeof(uint32_t));
     PA(pl->d_saw, std::max<uint64_t>(pl->saw_words, 8) * sizeof(float));
     PA(pl->d_err, 256);
+    PA(pl->d_pscan_status, 256 + 64 * pl->pscan_utt.size());
+    for (uint32_t u : pl->pscan_utt) {
+        const UttDev& U = pl->utts[u];
+        PScanDev S;
+        memset(&S, 0, sizeof S);
+        const uint64_t n = U.n_samples, nb = (n + 1 + SCAN_TILE - 1) / SCAN_TILE;
+        void *p = nullptr, *q = nullptr, *b = nullptr;
+        int rc1 = pool_alloc(ctx, (n + 1) * 8, &p);
+        if (!rc1) { pl->pscan_bufs.push_back(p); rc1 = pool_alloc(ctx, n * 8 + 8, &q); }
+        void *fl = nullptr, *bp = nullptr;
+        if (!rc1) { pl->pscan_bufs.push_back(q); rc1 = pool_alloc(ctx, nb * 8 + 8, &b); }
+        if (!rc1) { pl->pscan_bufs.push_back(b); rc1 = pool_alloc(ctx, n + 16, &fl); }
+        if (!rc1) { pl->pscan_bufs.push_back(fl); rc1 = pool_alloc(ctx, n / PS_BLOCK + 16, &bp); }
+        if (rc1) return fail(rc1);
+        pl->pscan_bufs.push_back(bp);
+        S.P = (unsigned long long*)p; S.inc = (unsigned long long*)q; S.bsum = (unsigned long long*)b;
+        S.sflag = (unsigned char*)fl; S.bpar = (unsigned char*)bp;
+        S.n = U.n_samples;
+        S.p0 = (unsigned long long)(U.init_phase * 1099511627776.0f);
+        pl->pscans.push_back(S);
+    }
     cudaStream_t s = ctx->stream;
     if (pl->n_elems) CUF(cudaMemcpyAsync(pl->d_elems, elems, (size_t)pl->n_elems * sizeof(grail_seq_elem), cudaMemcpyHostToDevice, s));
     CUF(cudaMemcpyAsync(pl->d_segs, pl->segs.data(), pl->segs.size() * sizeof(SegRec), cudaMemcpyHostToDevice, s));
@@ -504,6 +548,36 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
         pl->last_launches++;
     }
     CU(ctx, cudaEventRecord(pl->ev[2], s));
+    for (size_t i = 0; i < pl->pscans.size(); ++i) {
+        PScanDev S = pl->pscans[i];
+        const uint32_t u = pl->pscan_utt[i];
+        S.F = pl->d_F + pl->utts[u].f_off;
+        S.status = pl->d_pscan_status + 16 * i;
+        CU(ctx, cudaMemsetAsync(S.status, 0, 64, s));
+        const uint32_t n = S.n, nb = (uint32_t)(((uint64_t)n + 1 + SCAN_TILE - 1) / SCAN_TILE);
+        const uint32_t g256 = (n + 255) / 256;
+        auto scan = [&]() {
+            k_ps_scan_reduce<<<nb, SCAN_THREADS, 0, s>>>(S);
+            k_ps_scan_spine<<<1, 1024, 0, s>>>(S, nb);
+            k_ps_scan_apply<<<nb, SCAN_THREADS, 0, s>>>(S);
+        };
+        k_ps_init<<<g256, 256, 0, s>>>(S);
+        scan();                                            // round 0: unrounded prefix sum
+        pl->last_launches += 4;
+        for (int r = 0; r < PS_MAX_ROUNDS; ++r) {          // every kernel returns at once after convergence
+            const uint32_t nblk = (n + PS_BLOCK - 1) / PS_BLOCK;
+            k_ps_replay<<<(nblk + 127) / 128, 128, 0, s>>>(S);
+            k_ps_parity_block<<<(nblk + 127) / 128, 128, 0, s>>>(S);
+            k_ps_parity_spine<<<1, 1024, 0, s>>>(S, nblk);
+            k_ps_parity_fix<<<(nblk + 127) / 128, 128, 0, s>>>(S);
+            scan();
+            k_ps_verify<<<g256, 256, 0, s>>>(S);
+            k_ps_check<<<1, 1, 0, s>>>(S);
+            pl->last_launches += 9;
+        }
+        k_ps_saw<<<((n + 7) / 8 + 255) / 256, 256, 0, s>>>(S, P, u);
+        pl->last_launches++;
+    }
     if (pl->n_items) {
         k_phase_pair<<<(pl->n_utts + PH_UTTS - 1) / PH_UTTS, PH_UTTS * 64, 0, s>>>(P);
         pl->last_launches++;
@@ -630,6 +704,8 @@ int grail_cuda_set_option(grail_ctx* ctx, const char* key, double value)
     } else if (!strcmp(key, "formants_per_lane")) {
         if (value != 1.0 && value != 2.0) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "formants_per_lane must be 1 or 2");
         ctx->formants_per_lane = (int)value;
+    } else if (!strcmp(key, "pscan_min_samples")) {
+        ctx->pscan_min = value < 1.0 ? 1u : (value > 4.0e9 ? 0xFFFFFFFFu : (uint32_t)value);
     } else if (!strcmp(key, "zero_copy_out")) {
         ctx->zero_copy_out = value != 0.0;
     } else if (!strcmp(key, "debug_taps")) {
@@ -751,6 +827,29 @@ int grail_cuda_plan_timings(const grail_plan* plan, grail_timings* out)
     CU(ctx, cudaEventElapsedTime(&out->formant_ms, plan->ev[3], plan->ev[4]));
     CU(ctx, cudaEventElapsedTime(&out->total_ms, plan->ev[0], plan->ev[4]));
     out->n_launches = plan->last_launches;
+    return GRAIL_OK;
+}
+
+int grail_cuda_plan_phase_scan_stats(grail_plan* plan, uint32_t* stats)
+{
+    if (!plan || !stats) return GRAIL_ERR_INVALID_ARG;
+    grail_ctx* ctx = plan->ctx;
+    stats[0] = (uint32_t)plan->pscans.size();
+    stats[1] = stats[2] = stats[3] = 0;
+    if (plan->pscans.empty() || !plan->launched) return GRAIL_OK;
+    std::vector<uint32_t> st(16 * plan->pscans.size());
+    CU(ctx, cudaMemcpyAsync(st.data(), plan->d_pscan_status, st.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < plan->pscans.size(); ++i) {
+        stats[1] += st[16 * i + 1] ? 1u : 0u;
+        stats[2] = std::max(stats[2], st[16 * i + 2]);
+        stats[3] += st[16 * i + 3] ? 1u : 0u;
+        if (getenv("GRAIL_PSCAN_DEBUG")) {
+            fprintf(stderr, "pscan %zu: done %u rounds %u refused %u mismatches per round:", i, st[16 * i + 1], st[16 * i + 2], st[16 * i + 3]);
+            for (int r = 0; r < 12; ++r) fprintf(stderr, " %u", st[16 * i + 4 + r]);
+            fprintf(stderr, "\n");
+        }
+    }
     return GRAIL_OK;
 }
 

@@ -275,6 +275,12 @@ class Plan:
         self.ctx._check(self._L.grail_cuda_plan_timings(self._h, C.byref(t)))
         return {k: getattr(t, k) for k, _ in Timings._fields_}
 
+    def phase_scan_stats(self) -> dict:
+        """exact parallel phase scan of the last launch: scans, converged, max refinement rounds, refused"""
+        st = np.zeros(4, np.uint32)
+        self.ctx._check(self._L.grail_cuda_plan_phase_scan_stats(self._h, ptr(st)))
+        return {"scans": int(st[0]), "converged": int(st[1]), "max_rounds": int(st[2]), "refused": int(st[3])}
+
     def read_intermediates(self):
         """bit-exact taps: (F_t, carrier phase before each sample, polyBLEP saw), packed like the output"""
         n = self.total_samples

@@ -144,6 +144,11 @@ int  grail_cuda_plan_device_output(grail_plan* plan, int format, void** out_dptr
 /* D2H of the packed output into a host buffer (chunked, through pinned staging if pageable) */
 int  grail_cuda_plan_read_output(grail_plan* plan, int format, void* host_out);
 int  grail_cuda_plan_timings(const grail_plan* plan, grail_timings* out);
+/* Long utterances (>= option "pscan_min_samples", default 2^20) get their carrier phase from the exact parallel
+ * phase scan instead of the serial chain.  stats[4] = {scans in this plan, scans that converged (the rest fell back
+ * to the serial chain), largest number of refinement rounds used, scans refused (an F_t outside [2^-16, 0.5])}
+ * for the most recent launch. */
+int  grail_cuda_plan_phase_scan_stats(grail_plan* plan, uint32_t* stats);
 /* debug / parity taps, host buffers of total_samples entries; any may be NULL:
  * the bit-exact fundamental F_t, the carrier phase BEFORE each sample, and the polyBLEP saw */
 int  grail_cuda_plan_read_intermediates(grail_plan* plan, float* frequency, float* carrier_phase, float* saw);

@@ -24,7 +24,9 @@ def test_config3_long_form(ctx, oracle):
     assert plan.total_samples == 26457161
     plan.launch()
     out = plan.read_output()
-    print(plan.timings())
+    print(plan.timings(), plan.phase_scan_stats())
+    ps = plan.phase_scan_stats()
+    assert ps["scans"] == 1 and ps["converged"] == 1 and ps["refused"] == 0      # parallel-in-time phase, no serial chain
     f, ph, saw = plan.read_intermediates()
     want, tr, fin = oracle.synthesize(elems, vp[0], trace=True)
     assert np.array_equal(f.view(np.uint32), tr["frequency"].view(np.uint32))          # bit-exact fundamental
@@ -71,3 +73,30 @@ def test_config5_sample_rate_sweep(ctx, oracle, rate, count):
         st = W.parity_stats(out[oo[u]:oo[u + 1]], want)
         assert st["max_abs"] <= MAX_ABS and st["snr_db"] >= MIN_SNR_DB, (rate, u, st)
     plan.close()
+
+
+def test_parallel_phase_scan_matches_chain(ctx, oracle):
+    """the exact parallel phase scan (forced on short inputs) against the oracle's f32 chain, bit for bit: voiced,
+    silence-heavy (frequency 0.25: a wrap every 4 samples, exact ties on wrap steps) and random-pitch inputs"""
+    ctx.set_option("pscan_min_samples", 1)
+    try:
+        v = g.voices.generic()
+        cases = [W.from_phonemes([[0, 4, 3, 3, 4, 3]], v, [3]), W.from_phonemes([[0, 0, 0, 3, 0, 0, 4, 0]], v, [1]),
+                 W.config4(3, first_utt=500), W.config4(2, sample_rate=16000.0, first_utt=900)]
+        for elems, offs, vp in cases:
+            plan = ctx.plan(elems, offs, vp)
+            plan.launch()
+            out = plan.read_output()
+            ps = plan.phase_scan_stats()
+            assert ps["scans"] == len(offs) - 1 and ps["converged"] == ps["scans"], ps
+            f, ph, saw = plan.read_intermediates()
+            oo = plan.out_offsets
+            for u in range(len(offs) - 1):
+                want, tr, _ = oracle.synthesize(elems[offs[u]:offs[u + 1]], vp[u], trace=True)
+                assert np.array_equal(ph[oo[u]:oo[u + 1]].view(np.uint32), tr["carrier_phase"].view(np.uint32)), (u, ps)
+                st = W.parity_stats(out[oo[u]:oo[u + 1]], want)
+                assert st["max_abs"] <= MAX_ABS and st["snr_db"] >= MIN_SNR_DB, st
+            print(ps)
+            plan.close()
+    finally:
+        ctx.set_option("pscan_min_samples", 1 << 20)
