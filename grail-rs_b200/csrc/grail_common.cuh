@@ -278,14 +278,14 @@ struct JitRec {          // one per jitter period (value-noise wrap), shared by 
 // Wrap schedule of one value-noise phase clock over samples [0, n_max): rec[w] = {sample of the w-th wrap,
 // phase after it}; rec[0] is the initial period.  Returns the number of records, or 0 if `cap` is too small.
 // Shared by the host planner (few schedules) and k_jitter_schedule (many).
-GRAIL_HD uint32_t jitter_schedule_walk(float inc, uint32_t n_max, JitRec* rec, uint32_t cap)
+GRAIL_HD uint32_t jitter_schedule_walk(float inc, uint32_t n_max, JitRec* rec, uint32_t cap, float phase0 = 0.0f)
 {
     if (cap == 0) return 0;
     int64_t n = -1;
-    float ph = 0.0f;
+    float ph = phase0;   // value-noise phase before sample 0 (0 for a fresh Jitter, carried for a continued stream)
     uint32_t w = 0;
     rec[0].n = -1;
-    rec[0].phase = 0.0f;
+    rec[0].phase = phase0;
     const int64_t last = (int64_t)n_max - 1;
     while (n < last) {
         const ClockRun r = clock_asc_run(ph, inc, (uint64_t)(last - n));

@@ -38,10 +38,14 @@ struct UttDev {
     grail_voice_params voice;
     float    init_phase;           // carrier phase at sample 0 (0 for a fresh utterance)
     int32_t  pscan;                // >= 0: index of this utterance's exact parallel phase scan (long utterances)
+    uint32_t jw0;                  // value-noise wraps that happened before sample 0 (continued streams)
+    uint32_t has_init;             // filter states at sample 0 come from PlanDev::utt_init (continued streams)
+    uint64_t sample0;              // absolute index of sample 0 in its stream (aspiration-noise draw index)
 };
 
 struct JitSchedDev {
     float    inc;                  // voice.jitter_frequency
+    float    phase0;               // value-noise phase before sample 0
     uint32_t n_max;                // samples the schedule must cover
     uint32_t rec_first, rec_cap;   // slice of the JitRec array
     uint32_t n_recs;               // written by k_jitter_schedule
@@ -66,6 +70,8 @@ struct PlanDev {
     float*              saw;       // tiled: [group][j/8][lane][8]
     float*              phase_dbg; // optional linear carrier phase tap (same indexing as F), may be null
     uint32_t*           fflags;    // one word per 128 F_t entries: nonzero if any is negative or NaN
+    const float*        utt_init;  // per utterance 32 floats: a[8], b[8], c[8] at sample 0 (used when has_init)
+    float*              utt_final; // per utterance 32 floats: a[8], b[8], c[8] after the last sample, [24] = carrier phase
     const uint32_t*     pscan_status; // 16 words per parallel phase scan: {mismatches, done, rounds, unsupported, history[12]}
     uint32_t*           err;       // device error word
     uint32_t n_utts, n_items, n_groups, n_jscheds;
@@ -108,7 +114,7 @@ __global__ void k_jitter_schedule(PlanDev P)
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P.n_jscheds) return;
     JitSchedDev& S = P.jscheds[s];
-    const uint32_t n = jitter_schedule_walk(S.inc, S.n_max, P.jrecs + S.rec_first, S.rec_cap);
+    const uint32_t n = jitter_schedule_walk(S.inc, S.n_max, P.jrecs + S.rec_first, S.rec_cap, S.phase0);
     if (n == 0) {
         S.overflow = 1;
         S.n_recs = 1;
@@ -180,7 +186,7 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
     const JitRec* recs = P.jrecs + JS.rec_first;
     const uint32_t w = last_le(JS.n_recs, [&](uint32_t i) { return recs[i].n; }, (int64_t)ns);
     float jph = clock_asc_run(recs[w].phase, jinc, (uint64_t)((int64_t)ns - recs[w].n)).x;
-    uint32_t s_next = lcg_jump(U.voice.jitter_seed, jit_freq_cur_idx(w));
+    uint32_t s_next = lcg_jump(U.voice.jitter_seed, jit_freq_cur_idx((uint64_t)w + U.jw0));
     float cur = lcg_float(s_next);
     s_next = lcg_step(s_next);
     float nxt = lcg_float(s_next);
@@ -473,6 +479,7 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
             __syncwarp();
             if (lane0) mbar_arrive(full_a + buf * 8);   // release: the tile's phases (and its F stage) are ready
         }
+        if (lane0) P.utt_final[(size_t)u * 32 + 24] = phase;   // Synthesize.phase after the last sample (stream state)
     } else {
         // ---------------- saw warp ----------------
         float* dbg = P.phase_dbg ? P.phase_dbg + U.f_off : nullptr;
@@ -833,6 +840,7 @@ __global__ void k_ps_saw(PScanDev S, PlanDev P, uint32_t utt)
     if (!S.status[1]) return;                   // not converged: k_phase_pair does this utterance
     const uint32_t blk = blockIdx.x * blockDim.x + threadIdx.x;   // 8 samples per lane
     const uint64_t b0 = (uint64_t)blk * 8;
+    if (blk == 0) P.utt_final[(size_t)utt * 32 + 24] = __ull2float_rn(S.P[S.n]) * 9.094947017729282e-13f;
     if (b0 >= S.n) return;
     const UttDev& U = P.utts[utt];
     const uint32_t valid = (uint32_t)min((uint64_t)8, S.n - b0);
@@ -1077,7 +1085,8 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
         const JitRec* recs = P.jrecs + JS.rec_first;
         jw = last_le(JS.n_recs, [&](uint32_t i) { return recs[i].n; }, (int64_t)ns);
         jph = clock_asc_run(recs[jw].phase, jinc, (uint64_t)((int64_t)ns - recs[jw].n)).x;
-        s_noise = lcg_jump(U.voice.synth_seed, ns);   // noise of sample n is draw n+1  (:528)
+        jw += U.jw0;                                    // wraps since the Jitter was built, not since sample 0
+        s_noise = lcg_jump(U.voice.synth_seed, U.sample0 + ns);   // noise of stream sample n is draw n+1  (:528)
 #pragma unroll
         for (int j = 0; j < FPT; ++j) {
             if (L[j].fi < 0) continue;
@@ -1088,6 +1097,10 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
             L[j].xff = 0.f;
             fold_jitter(j, c0, lcg_float(L[j].s_ff), c1, lcg_float(L[j].s_amp));
             L[j].xff = 0.f; L[j].ff0 = dff * c0;      // base added by load_segment below
+            if (it.n0 == 0 && U.has_init) {           // a continued stream: the Synthesize filter states carry over
+                const float* st0 = P.utt_init + (size_t)it.utt * 32;
+                L[j].a = st0[L[j].fi]; L[j].b = st0[8 + L[j].fi]; L[j].c = st0[16 + L[j].fi];
+            }
         }
         load_segment();
     }
@@ -1176,6 +1189,7 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
     uint32_t lmax = 0;
 #pragma unroll 1
     for (int r = 0; r < 32; ++r) lmax = max(lmax, row_len[r]);
+    lmax = (lmax + 31u) & ~31u;      // whole 32-sample batches: the reduction runs at the end of each
 
     // saw source: walks the tiled layout from sample ns; crossing into the next chunk of the utterance (and,
     // at r == 0, into this lane's own chunk) is a pointer reset every CL samples
@@ -1219,7 +1233,9 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
         // Otherwise every parameter is linear in time over the block and the 7 per-sample coefficients are
         // interpolated between the block's end points (error ~ h^2/8 c'' ~ 1e-9 relative, far below f32 rounding),
         // which removes the blend / tan_approx / reciprocal work from 7 of every 8 samples.
-        const bool hand = act && !(time > quiet_t);
+        // (the ragged last block of a chunk also goes through the per-sample loop, so that the lane stops exactly
+        //  after its last sample: a continued stream picks the filter states up from there)
+        const bool hand = act && (!(time > quiet_t) || r + 8 > r_hi);
         const float a_now = time * inv_bl, a_end = fmaf(8.0f, ndt, time) * inv_bl;
         const bool kink = act && !hand && (!(jph < quiet_j) || ((a_now > 1.0f) != (a_end > 1.0f)));
         const bool warp_exact = __any_sync(0xffffffffu, kink);
@@ -1279,8 +1295,9 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
             } else {
                 // the phoneme's last samples: generic per-sample loop (results parked in the smem row)
                 c_valid = false;
+                const int cnt = min(8, r_hi - r);
 #pragma unroll 1
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < cnt; ++k) {
                     const float4 q = k < 4 ? sa : sb;
                     const int kk = k & 3;
                     const float s = kk == 0 ? q.x : (kk == 1 ? q.y : (kk == 2 ? q.z : q.w));
@@ -1350,6 +1367,13 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
                 __syncthreads();
             }
         }
+    }
+    // the lane that owns an utterance's last chunk leaves the Synthesize filter states behind (stream state)
+    if (on && it.n0 + it.len == U.n_samples) {
+        float* fin = P.utt_final + (size_t)it.utt * 32;
+#pragma unroll
+        for (int j = 0; j < FPT; ++j)
+            if (L[j].fi >= 0) { fin[L[j].fi] = L[j].a; fin[8 + L[j].fi] = L[j].b; fin[16 + L[j].fi] = L[j].c; }
     }
 }
 

@@ -129,6 +129,7 @@ struct grail_plan {
     float* d_elems = nullptr; SegRec* d_segs = nullptr; UttDev* d_utts = nullptr; ItemDev* d_items = nullptr;
     JitSchedDev* d_jscheds = nullptr; JitRec* d_jrecs = nullptr; float* d_F = nullptr; float* d_saw = nullptr;
     float* d_phase_dbg = nullptr; uint32_t* d_err = nullptr; uint32_t* d_fflags = nullptr;
+    float* d_utt_init = nullptr; float* d_utt_final = nullptr;
     void* d_out = nullptr; size_t d_out_bytes = 0; int d_out_format = -1;
     cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
     bool launched = false;
@@ -160,15 +161,33 @@ typedef std::unordered_map<SeqKey, SeqVal, SeqKeyHash> SeqCache;
 
 static const uint64_t MAX_UTT_SAMPLES = (1ull << 31) - 4096;
 
+// How a single-utterance plan continues a stream (grail_stream): the three iterators' carried state.
+struct StreamStart {
+    bool     cont_phoneme = false;  // elems[0] is a phoneme already in progress ...
+    float    time0 = 0.0f;          //   ... whose Sequencer.time at the window's first sample is this
+    float    t_neg = 0.0f;          // else: the (negative) Sequencer.time carried into elems[0]'s hand-over
+    bool     fresh = true;          // the very first window: t_neg = 0 - delta_time
+    float    jitter_phase = 0.0f;   // value-noise phase after the last produced sample
+    uint32_t jitter_wraps = 0;      // value-noise wraps so far
+    uint64_t sample0 = 0;           // absolute index of the window's first sample
+    float    carrier_phase = 0.0f;  // Synthesize.phase
+    const float* filter_state = nullptr;   // 24 floats a[8] b[8] c[8], or null (all zero)
+    uint64_t max_samples = ~0ull;   // truncate the window here
+    bool     finished = true;       // false: the last element is only a look-ahead, its own samples are not due yet
+};
+
+
 static int64_t schedule_utterance(const grail_seq_elem* e, uint32_t n_elems, float sample_rate, SegRec* segs,
-                                  SeqCache& cache)
+                                  SeqCache& cache, const StreamStart* ss = nullptr, float* t_neg_out = nullptr)
 {
     const float dt = sdiv(1.0f, sample_rate);       // src/lib.rs:944
     float t_neg = ssub(0.0f, dt);                   // first call: time = 0 - delta_time  (:861)
+    if (ss && !ss->fresh) t_neg = ss->t_neg;
     uint64_t n = 0;
     for (uint32_t p = 0; p < n_elems; ++p) {
         const float len = e[p].length;
-        const float time0 = sadd(t_neg, len);       // :873 / :882
+        float time0 = sadd(t_neg, len);             // :873 / :882
+        if (p == 0 && ss && ss->cont_phoneme) time0 = ss->time0;   // a phoneme already in progress
         if (segs) { segs[p].start = (uint32_t)n; segs[p].time0 = time0; }
         const SeqKey key = { f2u(time0), 0u, f2u(dt) };
         auto itc = cache.find(key);
@@ -186,6 +205,7 @@ static int64_t schedule_utterance(const grail_seq_elem* e, uint32_t n_elems, flo
         if (n > MAX_UTT_SAMPLES) return -1;
         t_neg = u2f(v.x);
     }
+    if (t_neg_out) *t_neg_out = t_neg;
     return (int64_t)n;
 }
 
@@ -283,6 +303,8 @@ static PlanDev plan_dev(const grail_plan* pl, bool with_dbg)
     P.err = pl->d_err;
     P.fflags = pl->d_fflags;
     P.pscan_status = pl->d_pscan_status;
+    P.utt_init = pl->d_utt_init;
+    P.utt_final = pl->d_utt_final;
     P.n_utts = pl->n_utts; P.n_items = pl->n_items; P.n_groups = pl->n_groups; P.n_jscheds = pl->n_jscheds;
     P.chunk_len = pl->chunk_len;
     P.warmup_nepers = (float)pl->ctx->warmup_nepers;
@@ -294,7 +316,7 @@ static void plan_release(grail_plan* pl)
     if (!pl) return;
     grail_ctx* ctx = pl->ctx;
     void* bufs[] = { pl->d_elems, pl->d_segs, pl->d_utts, pl->d_items, pl->d_jscheds, pl->d_jrecs, pl->d_F, pl->d_saw,
-                     pl->d_phase_dbg, pl->d_err, pl->d_out, pl->d_fflags };
+                     pl->d_phase_dbg, pl->d_err, pl->d_out, pl->d_fflags, pl->d_utt_init, pl->d_utt_final };
     for (void* b : bufs) pool_free(ctx, b);
     for (void* b : pl->pscan_bufs) pool_free(ctx, b);
     pool_free(ctx, pl->d_pscan_status);
@@ -304,8 +326,10 @@ static void plan_release(grail_plan* pl)
 }
 
 static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_t* utt_offsets,
-                      const grail_voice_params* voices, uint32_t n_utts, grail_plan** out_plan)
+                      const grail_voice_params* voices, uint32_t n_utts, grail_plan** out_plan,
+                      const StreamStart* ss = nullptr)
 {
+    if (ss && n_utts != 1) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "a stream window is one utterance");
     int rc = validate_inputs(ctx, elems, utt_offsets, voices, n_utts);
     if (rc) return rc;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -330,7 +354,12 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
         U.elem_first = utt_offsets[u];
         U.n_elems = utt_offsets[u + 1] - utt_offsets[u];
         const grail_seq_elem* e = elems + U.elem_first;
-        const int64_t n = schedule_utterance(e, U.n_elems, voices[u].sample_rate, pl->segs.data() + U.elem_first, cache);
+        int64_t n = schedule_utterance(e, U.n_elems, voices[u].sample_rate, pl->segs.data() + U.elem_first, cache, ss);
+        if (n >= 0 && ss) {
+            // an unfinished stream holds its last element back as look-ahead: only the phonemes before it are due
+            if (!ss->finished && U.n_elems > 0) n = (int64_t)pl->segs[U.elem_first + U.n_elems - 1].start;
+            if ((uint64_t)n > ss->max_samples) n = (int64_t)ss->max_samples;
+        }
         if (n < 0) {
             plan_release(pl);
             return set_err(ctx, GRAIL_ERR_UNSUPPORTED,
@@ -339,8 +368,11 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
         }
         U.n_samples = (uint32_t)n;
         U.voice = voices[u];
-        U.init_phase = 0.0f;
+        U.init_phase = ss ? ss->carrier_phase : 0.0f;
         U.pscan = -1;
+        U.jw0 = ss ? ss->jitter_wraps : 0u;
+        U.sample0 = ss ? ss->sample0 : 0ull;
+        U.has_init = (ss && ss->filter_state) ? 1u : 0u;
         U.out_off = total;
         U.f_off = f_words;
         total += (uint64_t)n;
@@ -352,6 +384,9 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
             bool act = false;
             for (uint32_t p = 0; p < U.n_elems && !act; ++p)
                 act = e[p].has_elem && !(e[p].elem.formant_amp[i] == 0.0f);
+            // a continued stream: a formant that is still ringing stays active whatever the new elements say
+            if (ss && ss->filter_state)
+                act = act || ss->filter_state[i] != 0.0f || ss->filter_state[8 + i] != 0.0f || ss->filter_state[16 + i] != 0.0f;
             if (act) U.active[U.n_active++] = (uint8_t)i;
         }
         nw = std::max(nw, U.n_active);
@@ -362,6 +397,7 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
             JitSchedDev js;
             memset(&js, 0, sizeof js);
             js.inc = voices[u].jitter_frequency;
+            js.phase0 = ss ? ss->jitter_phase : 0.0f;
             js.n_max = U.n_samples;
             jmap.emplace(key, (uint32_t)pl->jscheds.size());
             U.jit_sched = (uint32_t)pl->jscheds.size();
@@ -394,7 +430,7 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
         pl->jit_on_host = true;
         pl->jrecs.resize(std::max<uint32_t>(pl->n_jrecs, 1));
         for (auto& js : pl->jscheds) {
-            js.n_recs = jitter_schedule_walk(js.inc, js.n_max, pl->jrecs.data() + js.rec_first, js.rec_cap);
+            js.n_recs = jitter_schedule_walk(js.inc, js.n_max, pl->jrecs.data() + js.rec_first, js.rec_cap, js.phase0);
             if (js.n_recs == 0) {
                 plan_release(pl);
                 return set_err(ctx, GRAIL_ERR_UNSUPPORTED, "jitter schedule overflow");
@@ -489,6 +525,8 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
     PA(pl->d_fflags, (pl->f_words / 128 + 2) * sizeof(uint32_t));
     PA(pl->d_saw, std::max<uint64_t>(pl->saw_words, 8) * sizeof(float));
     PA(pl->d_err, 256);
+    PA(pl->d_utt_final, std::max<size_t>(n_utts, 1) * 32 * sizeof(float));
+    PA(pl->d_utt_init, std::max<size_t>(n_utts, 1) * 32 * sizeof(float));
     PA(pl->d_pscan_status, 256 + 64 * pl->pscan_utt.size());
     for (uint32_t u : pl->pscan_utt) {
         const UttDev& U = pl->utts[u];
@@ -517,6 +555,17 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
     if (pl->n_items) CUF(cudaMemcpyAsync(pl->d_items, pl->items.data(), pl->n_items * sizeof(ItemDev), cudaMemcpyHostToDevice, s));
     if (pl->n_jscheds) CUF(cudaMemcpyAsync(pl->d_jscheds, pl->jscheds.data(), pl->n_jscheds * sizeof(JitSchedDev), cudaMemcpyHostToDevice, s));
     if (pl->jit_on_host && pl->n_jrecs) CUF(cudaMemcpyAsync(pl->d_jrecs, pl->jrecs.data(), (size_t)pl->n_jrecs * sizeof(JitRec), cudaMemcpyHostToDevice, s));
+    {
+        float init[32];
+        memset(init, 0, sizeof init);
+        if (ss && ss->filter_state) memcpy(init, ss->filter_state, 24 * sizeof(float));
+        CUF(cudaMemsetAsync(pl->d_utt_init, 0, std::max<size_t>(n_utts, 1) * 32 * sizeof(float), s));
+        CUF(cudaMemsetAsync(pl->d_utt_final, 0, std::max<size_t>(n_utts, 1) * 32 * sizeof(float), s));
+        if (ss) {   // formants nobody touches in this window keep their carried state
+            CUF(cudaMemcpyAsync(pl->d_utt_init, init, sizeof init, cudaMemcpyHostToDevice, s));
+            CUF(cudaMemcpyAsync(pl->d_utt_final, init, sizeof init, cudaMemcpyHostToDevice, s));
+        }
+    }
     for (auto& e : pl->ev) CUF(cudaEventCreate(&e));
     // the host vectors are read by the async copies above: make them safe to outlive this call
     CUF(cudaStreamSynchronize(s));
@@ -942,26 +991,134 @@ int grail_cuda_synthesize_batch(grail_ctx* ctx, const grail_seq_elem* elems, con
     return rc;
 }
 
-// ---- streaming: declared in the ABI; the carried-state kernels land in a later milestone ----------
+// ---- streaming ---------------------------------------------------------------------------------
+// A grail_stream is the Copy-able state of the reference's three iterators: Sequencer
+// {cur, next, time}, Jitter {value-noise phase, wrap count, seed}, Synthesize {carrier phase, a, b, c, noise draw
+// index}.  Each pull synthesizes one window of the unbounded utterance with the batch kernels, entering them with
+// that state and reading it back afterwards, so a stream pulled in any window sizes equals the one-shot result
+// (bit-exact clocks / phase; filters continue from their exact states, no warm-up at the window edge).
+} // extern "C"
+
+struct grail_stream {
+    grail_ctx* ctx = nullptr;
+    grail_voice_params voice{};
+    std::vector<grail_seq_elem> pending;   // [0] = the phoneme in progress (or the next one to start)
+    bool finished = false, ended = false;
+    StreamStart st;                        // state entering the next window
+    float filter[24];
+};
+
+extern "C" {
+
 int grail_cuda_stream_new(grail_ctx* ctx, const grail_voice_params* voice, grail_stream** out_stream)
 {
-    (void)voice;
-    if (out_stream) *out_stream = nullptr;
-    return set_err(ctx, GRAIL_ERR_UNSUPPORTED, "streaming is not implemented in this build");
+    if (!ctx || !voice || !out_stream) return GRAIL_ERR_INVALID_ARG;
+    *out_stream = nullptr;
+    const uint32_t offs[2] = { 0, 0 };
+    int rc = validate_inputs(ctx, nullptr, offs, voice, 1);
+    if (rc) return rc;
+    grail_stream* s = new (std::nothrow) grail_stream();
+    if (!s) return set_err(ctx, GRAIL_ERR_OOM, "host allocation failed");
+    s->ctx = ctx;
+    s->voice = *voice;
+    memset(s->filter, 0, sizeof s->filter);
+    *out_stream = s;
+    return GRAIL_OK;
 }
+
 int grail_cuda_stream_push(grail_stream* s, const grail_seq_elem* elems, uint32_t n_elems)
 {
-    (void)s; (void)elems; (void)n_elems;
-    return GRAIL_ERR_UNSUPPORTED;
+    if (!s || (n_elems && !elems)) return GRAIL_ERR_INVALID_ARG;
+    if (s->finished) return set_err(s->ctx, GRAIL_ERR_INVALID_ARG, "stream already finished");
+    for (uint32_t i = 0; i < n_elems; ++i)
+        if (!std::isfinite(elems[i].length)) return set_err(s->ctx, GRAIL_ERR_INVALID_ARG, "non-finite phoneme length");
+    s->pending.insert(s->pending.end(), elems, elems + n_elems);
+    return GRAIL_OK;
 }
-int grail_cuda_stream_finish(grail_stream* s) { (void)s; return GRAIL_ERR_UNSUPPORTED; }
+
+int grail_cuda_stream_finish(grail_stream* s)
+{
+    if (!s) return GRAIL_ERR_INVALID_ARG;
+    s->finished = true;
+    return GRAIL_OK;
+}
+
 int grail_cuda_stream_pull(grail_stream* s, float* out, uint64_t max_samples, uint64_t* n_written)
 {
-    (void)s; (void)out; (void)max_samples;
-    if (n_written) *n_written = 0;
-    return GRAIL_ERR_UNSUPPORTED;
+    if (!s || !n_written || (max_samples && !out)) return GRAIL_ERR_INVALID_ARG;
+    *n_written = 0;
+    grail_ctx* ctx = s->ctx;
+    if (s->ended || max_samples == 0 || s->pending.empty()) {
+        if (s->finished && s->pending.empty()) s->ended = true;
+        return GRAIL_OK;
+    }
+    if (!s->finished && s->pending.size() < 2) return GRAIL_OK;   // the only element is still just a look-ahead
+    StreamStart ss = s->st;
+    ss.filter_state = s->st.fresh ? nullptr : s->filter;
+    ss.max_samples = std::min<uint64_t>(max_samples, MAX_UTT_SAMPLES);
+    ss.finished = s->finished;
+    const uint32_t offs[2] = { 0u, (uint32_t)s->pending.size() };
+    grail_plan* pl = nullptr;
+    int rc = plan_build(ctx, s->pending.data(), offs, &s->voice, 1, &pl, &ss);
+    if (rc) return rc;
+    const uint64_t n = pl->total_samples;
+    if (n == 0) {
+        plan_release(pl);
+        if (s->finished) { s->ended = true; s->pending.clear(); }
+        return GRAIL_OK;
+    }
+    void* d = nullptr;
+    rc = grail_cuda_plan_device_output(pl, GRAIL_F32, &d);
+    if (!rc) rc = plan_enqueue(pl, d, GRAIL_F32, false, true);
+    float fin[32];
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(fin, pl->d_utt_final, sizeof fin, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) rc = set_err(ctx, GRAIL_ERR_CUDA, "state read-back failed: %s", cudaGetErrorString(e));
+    }
+    if (!rc) rc = grail_cuda_plan_read_output(pl, GRAIL_F32, out);    // synchronizes the stream
+    if (rc) {
+        cudaStreamSynchronize(ctx->stream);
+        plan_release(pl);
+        return rc;
+    }
+    // ---- the iterators' state after sample n-1, from the exact host-side schedules
+    const float dt = sdiv(1.0f, s->voice.sample_rate);
+    const uint32_t last = (uint32_t)(n - 1);
+    uint32_t p = 0;
+    while (p + 1 < pl->utts[0].n_elems && pl->segs[p + 1].start <= last) ++p;
+    const float time_last = clock_desc_run(pl->segs[p].time0, dt, last - pl->segs[p].start).x;
+    const JitSchedDev& js = pl->jscheds[0];
+    uint32_t w = 0;
+    while (w + 1 < js.n_recs && pl->jrecs[js.rec_first + w + 1].n <= (int32_t)last) ++w;
+    const JitRec& jr = pl->jrecs[js.rec_first + w];
+    StreamStart nx;
+    nx.fresh = false;
+    nx.jitter_phase = clock_asc_run(jr.phase, s->voice.jitter_frequency, (uint64_t)((int64_t)last - jr.n)).x;
+    nx.jitter_wraps = s->st.jitter_wraps + w;
+    nx.sample0 = s->st.sample0 + n;
+    nx.carrier_phase = fin[24];
+    memcpy(s->filter, fin, sizeof s->filter);
+    // Sequencer: what the next call to next() will do with `time` (src/lib.rs:861-888)
+    const float t_next = ssub(time_last, dt);
+    uint32_t consumed;
+    if (t_next < 0.0f) {            // the hand-over happens on the next sample: phoneme p is done
+        nx.cont_phoneme = false;
+        nx.t_neg = t_next;
+        consumed = p + 1;
+    } else {                        // phoneme p continues
+        nx.cont_phoneme = true;
+        nx.time0 = t_next;
+        consumed = p;
+    }
+    s->pending.erase(s->pending.begin(), s->pending.begin() + consumed);
+    s->st = nx;
+    if (s->finished && s->pending.empty()) s->ended = true;
+    plan_release(pl);
+    *n_written = n;
+    return GRAIL_OK;
 }
-void grail_cuda_stream_free(grail_stream* s) { (void)s; }
+
+void grail_cuda_stream_free(grail_stream* s) { delete s; }
 
 // ---- roofline probes ---------------------------------------------------------------------------
 int grail_cuda_probe_fp32_peak(grail_ctx* ctx, double* ffma_flops, double* mufu_ops, double* sm_mhz_effective)

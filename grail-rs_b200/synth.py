@@ -227,6 +227,9 @@ class Context:
     def plan(self, elems: np.ndarray, utt_offsets: np.ndarray, voices: np.ndarray) -> "Plan":
         return Plan(self, elems, utt_offsets, voices)
 
+    def stream(self, voice_params: np.ndarray) -> "Stream":
+        return Stream(self, voice_params)
+
 
 class Plan:
     """a batch resident in HBM (grail_plan): upload once, launch many times"""
@@ -287,6 +290,40 @@ class Plan:
         f, p, s = (np.zeros(n, np.float32) for _ in range(3))
         self.ctx._check(self._L.grail_cuda_plan_read_intermediates(self._h, ptr(f), ptr(p), ptr(s)))
         return f, p, s
+
+
+class Stream:
+    """one unbounded utterance with carried iterator state (grail_stream): the drop-in for pulling the reference's
+    iterator chain from an audio callback (examples/interactive.rs:31-69)"""
+
+    def __init__(self, ctx: Context, voice_params: np.ndarray):
+        self.ctx = ctx
+        self._L = ctx._L
+        v = np.ascontiguousarray(voice_params, VOICE_DT).reshape(-1)[:1].copy()
+        h = C.c_void_p()
+        ctx._check(self._L.grail_cuda_stream_new(ctx._h, ptr(v), C.byref(h)))
+        self._h = h
+
+    def push(self, elems: np.ndarray):
+        e = np.ascontiguousarray(elems, SEQ_ELEM_DT).reshape(-1)
+        self.ctx._check(self._L.grail_cuda_stream_push(self._h, ptr(e), len(e)))
+
+    def finish(self):
+        self.ctx._check(self._L.grail_cuda_stream_finish(self._h))
+
+    def pull(self, max_samples: int) -> np.ndarray:
+        """up to max_samples more samples; fewer (possibly none) when the upstream has run dry"""
+        out = np.empty(int(max_samples), np.float32)
+        n = C.c_uint64(0)
+        self.ctx._check(self._L.grail_cuda_stream_pull(self._h, ptr(out), int(max_samples), C.byref(n)))
+        return out[: n.value]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.grail_cuda_stream_free(self._h)
+            self._h = None
+
+    __del__ = close
 
 
 def count_samples(elems: np.ndarray, utt_offsets: np.ndarray, voices: np.ndarray) -> np.ndarray:

@@ -158,7 +158,9 @@ int  grail_cuda_plan_read_intermediates(grail_plan* plan, float* frequency, floa
  * Jitter{3 generators}, Synthesize{phase, a, b, c, seed}).  push appends
  * upstream SequenceElems; pull synthesizes up to max_samples more samples and returns how many
  * were produced (fewer only when the upstream ran dry: the last pushed element is held back as
- * `next` until another element or grail_cuda_stream_finish arrives). */
+ * `next` until another element or grail_cuda_stream_finish arrives).  `out` is a host buffer.  A stream pulled in
+ * windows of any size reproduces the one-shot result: clocks, F_t and carrier phase bit for bit, the filters continue
+ * from their exact states. */
 int  grail_cuda_stream_new(grail_ctx* ctx, const grail_voice_params* voice, grail_stream** out_stream);
 int  grail_cuda_stream_push(grail_stream* s, const grail_seq_elem* elems, uint32_t n_elems);
 int  grail_cuda_stream_finish(grail_stream* s);

@@ -1,0 +1,65 @@
+"""Streaming (unbounded upstream, examples/interactive.rs): a stream pulled in arbitrary windows equals the one-shot
+result; the last pushed element is held back as look-ahead until more input or finish() arrives."""
+import numpy as np
+import pytest
+
+import grail_rs_b200 as g
+from grail_rs_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = g.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("windows", [[1 << 30], [4096] * 200, [777, 10000, 1, 255, 256, 257, 50000] * 40, [22047, 22048, 1] * 40])
+def test_stream_equals_one_shot(ctx, oracle, windows):
+    phon = [0, 4, 3, 0, 0, 3, 4, 4]
+    elems, offs, vp = W.from_phonemes([phon], g.voices.generic(), [11])
+    elems = elems.copy()
+    elems["length"] = np.array([0.5, 0.3, 0.5, 0.11, 0.5, 0.25, 0.5, 0.4], np.float32)
+    want, _, _ = oracle.synthesize(elems, vp[0])
+    st = ctx.stream(vp[0])
+    st.push(elems)
+    st.finish()
+    got = []
+    for wlen in windows:
+        x = st.pull(wlen)
+        if len(x) == 0:
+            break
+        assert len(x) <= wlen
+        got.append(x.copy())
+    got = np.concatenate(got)
+    assert len(got) == len(want)
+    stats = W.parity_stats(got, want)
+    assert stats["max_abs"] <= 1e-4 and stats["snr_db"] >= 90.0, stats
+    assert len(st.pull(100)) == 0          # the iterator is exhausted
+    st.close()
+
+
+def test_stream_incremental_push_holds_lookahead(ctx, oracle):
+    v = g.voices.generic()
+    phon = [0, 3, 4, 3]
+    elems, offs, vp = W.from_phonemes([phon], v, [5])
+    want, tr, _ = oracle.synthesize(elems, vp[0], trace=True)
+    bounds = [0] + list(np.flatnonzero(np.diff(tr["phoneme_index"])) + 1) + [len(want)]
+    st = ctx.stream(vp[0])
+    st.push(elems[:1])
+    assert len(st.pull(1 << 20)) == 0                       # one element: it is only the look-ahead so far
+    got = []
+    for k in range(1, len(phon)):
+        st.push(elems[k:k + 1])
+        x = st.pull(1 << 20)
+        assert len(x) == bounds[k] - bounds[k - 1]           # exactly phoneme k-1 becomes available
+        got.append(x.copy())
+    st.finish()
+    got.append(st.pull(1 << 20).copy())
+    got = np.concatenate(got)
+    assert len(got) == len(want)
+    stats = W.parity_stats(got, want)
+    assert stats["max_abs"] <= 1e-4 and stats["snr_db"] >= 90.0, stats
+    st.close()
