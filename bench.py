@@ -210,6 +210,7 @@ def run_ours(args):
     for _ in range(args.steps):
         plan.launch(d_out)
         launches += 3
+    plan.join()                      # the main stream waits for the pipelined launches before the end event
     e1.record(stream)
     e1.synchronize()
     barrier()

@@ -30,7 +30,10 @@ struct PoolBuf {
 
 struct grail_ctx {
     int            device = 0;
-    cudaStream_t   stream = nullptr;
+    cudaStream_t   stream = nullptr;    // main (API-visible) stream
+    cudaStream_t   s_front = nullptr;   // pipelined plans: schedule / frequency / phase kernels of launch k+1 ...
+    cudaStream_t   s_back = nullptr;    // ... overlap the formant kernel of launch k
+    int            pipeline = 0;        // ctx option "pipeline" (off: measured no gain, the chains starve under k_formant)
     cudaDeviceProp prop{};
     std::string    err;
     std::vector<PoolBuf> pool;
@@ -132,6 +135,17 @@ struct grail_plan {
     float* d_utt_init = nullptr; float* d_utt_final = nullptr;
     void* d_out = nullptr; size_t d_out_bytes = 0; int d_out_format = -1;
     cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+    // Pipelined plans (grail_cuda_plan_create with ctx option "pipeline"): two scratch sets, so that the front
+    // kernels of launch k+1 (own stream) run under the formant kernel of launch k.  Slot 0 is d_F/d_fflags/d_saw.
+    struct Slot {
+        float* F = nullptr; uint32_t* fflags = nullptr; float* saw = nullptr;
+        cudaEvent_t front_done = nullptr, back_done = nullptr;
+        cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+        bool used = false;
+    } slot[2];
+    bool pipelined = false, in_flight = false;
+    uint32_t launch_idx = 0, last_slot = 0;
+    cudaEvent_t ev_begin = nullptr;
     bool launched = false;
     std::vector<PScanDev> pscans;          // exact parallel phase scans (one per long utterance)
     std::vector<uint32_t> pscan_utt;
@@ -294,14 +308,14 @@ static void launch_formant_of(int nw, int fpt, const PlanDev& P, void* out, int 
     }
 }
 
-static PlanDev plan_dev(const grail_plan* pl, bool with_dbg)
+static PlanDev plan_dev(const grail_plan* pl, bool with_dbg, int slot = 0)
 {
     PlanDev P;
     P.elems = pl->d_elems; P.segs = pl->d_segs; P.utts = pl->d_utts; P.items = pl->d_items;
-    P.jscheds = pl->d_jscheds; P.jrecs = pl->d_jrecs; P.F = pl->d_F; P.saw = pl->d_saw;
+    P.jscheds = pl->d_jscheds; P.jrecs = pl->d_jrecs; P.F = pl->slot[slot].F; P.saw = pl->slot[slot].saw;
     P.phase_dbg = with_dbg ? pl->d_phase_dbg : nullptr;
     P.err = pl->d_err;
-    P.fflags = pl->d_fflags;
+    P.fflags = pl->slot[slot].fflags;
     P.pscan_status = pl->d_pscan_status;
     P.utt_init = pl->d_utt_init;
     P.utt_final = pl->d_utt_final;
@@ -319,6 +333,13 @@ static void plan_release(grail_plan* pl)
                      pl->d_phase_dbg, pl->d_err, pl->d_out, pl->d_fflags, pl->d_utt_init, pl->d_utt_final };
     for (void* b : bufs) pool_free(ctx, b);
     for (void* b : pl->pscan_bufs) pool_free(ctx, b);
+    pool_free(ctx, pl->slot[1].F); pool_free(ctx, pl->slot[1].fflags); pool_free(ctx, pl->slot[1].saw);
+    for (auto& sl : pl->slot) {
+        if (sl.front_done) cudaEventDestroy(sl.front_done);
+        if (sl.back_done) cudaEventDestroy(sl.back_done);
+        for (auto& e : sl.ev) if (e) cudaEventDestroy(e);
+    }
+    if (pl->ev_begin) cudaEventDestroy(pl->ev_begin);
     pool_free(ctx, pl->d_pscan_status);
     for (auto& e : pl->ev)
         if (e) cudaEventDestroy(e);
@@ -327,7 +348,7 @@ static void plan_release(grail_plan* pl)
 
 static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_t* utt_offsets,
                       const grail_voice_params* voices, uint32_t n_utts, grail_plan** out_plan,
-                      const StreamStart* ss = nullptr)
+                      const StreamStart* ss = nullptr, bool pipelined = false)
 {
     if (ss && n_utts != 1) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "a stream window is one utterance");
     int rc = validate_inputs(ctx, elems, utt_offsets, voices, n_utts);
@@ -336,6 +357,7 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
     grail_plan* pl = new (std::nothrow) grail_plan();
     if (!pl) return set_err(ctx, GRAIL_ERR_OOM, "host allocation failed");
     pl->ctx = ctx;
+    pl->pipelined = pipelined && ctx->pipeline;
     pl->n_utts = n_utts;
     pl->n_elems = n_utts ? utt_offsets[n_utts] : 0;
     pl->utts.resize(n_utts);
@@ -443,6 +465,13 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
     if (target == 0) {
         int occ = formant_occupancy_of((int)nw, (int)pl->fpt);
         if (occ < 1) occ = 1;
+        if (pl->pipelined) {
+            // leave room on every SM for the next launch's phase kernel (2 warps per utterance, all utterances
+            // resident at once: ~32K registers) so that it really runs under this launch's formant kernel
+            const int cta_regs = std::max(1, 65536 / occ);
+            const int reserve = (32768 + cta_regs - 1) / cta_regs;
+            occ = std::max(occ - reserve, (occ + 1) / 2);
+        }
         target = (uint64_t)ctx->prop.multiProcessorCount * (uint64_t)occ * 32ull;
     }
     // smallest chunk length (multiple of 32) whose work items still fit in `target` lanes: the grid is then a
@@ -567,6 +596,18 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
         }
     }
     for (auto& e : pl->ev) CUF(cudaEventCreate(&e));
+    pl->slot[0].F = pl->d_F; pl->slot[0].fflags = pl->d_fflags; pl->slot[0].saw = pl->d_saw;
+    if (pl->pipelined) {
+        PA(pl->slot[1].F, pl->f_words * sizeof(float));
+        PA(pl->slot[1].fflags, (pl->f_words / 128 + 2) * sizeof(uint32_t));
+        PA(pl->slot[1].saw, std::max<uint64_t>(pl->saw_words, 8) * sizeof(float));
+        CUF(cudaEventCreateWithFlags(&pl->ev_begin, cudaEventDisableTiming));
+        for (auto& sl : pl->slot) {
+            CUF(cudaEventCreateWithFlags(&sl.front_done, cudaEventDisableTiming));
+            CUF(cudaEventCreateWithFlags(&sl.back_done, cudaEventDisableTiming));
+            for (auto& e : sl.ev) CUF(cudaEventCreate(&e));
+        }
+    }
     // the host vectors are read by the async copies above: make them safe to outlive this call
     CUF(cudaStreamSynchronize(s));
 #undef PA
@@ -575,32 +616,67 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
     return GRAIL_OK;
 }
 
+// make the ctx's main stream wait for everything this plan has in flight on the pipeline streams
+static int plan_join(grail_plan* pl)
+{
+    grail_ctx* ctx = pl->ctx;
+    if (pl->pipelined && pl->in_flight) {
+        const grail_plan::Slot& sl = pl->slot[pl->last_slot];
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, sl.front_done, 0));
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, sl.back_done, 0));
+        pl->in_flight = false;
+    }
+    return GRAIL_OK;
+}
+
 static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, bool formant)
 {
     grail_ctx* ctx = pl->ctx;
     if (format != GRAIL_F32 && format != GRAIL_I16) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "unknown sample format");
     CU(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream;
-    const PlanDev P = plan_dev(pl, with_dbg);
+    // Stream layout.  Plain plans run the whole path on the main stream.  Pipelined plans alternate between two
+    // scratch sets: the front kernels (schedule, frequency, phase) go to s_front, the formant kernel to s_back, so
+    // the latency-bound phase chains of launch k+1 execute in the shadow of launch k's formant kernel.
+    const bool pipe = pl->pipelined && !with_dbg && formant;
+    int slot = 0;
+    cudaStream_t sf = ctx->stream, sb = ctx->stream;
+    cudaEvent_t* ev = pl->ev;
+    if (pipe) {
+        slot = (int)(pl->launch_idx++ & 1u);
+        grail_plan::Slot& sl = pl->slot[slot];
+        sf = ctx->s_front;
+        sb = ctx->s_back;
+        ev = sl.ev;
+        if (!pl->in_flight) {   // first launch of a burst: order it after what the caller queued on the main stream
+            CU(ctx, cudaEventRecord(pl->ev_begin, ctx->stream));
+            CU(ctx, cudaStreamWaitEvent(sf, pl->ev_begin, 0));
+        }
+        if (sl.used) CU(ctx, cudaStreamWaitEvent(sf, sl.back_done, 0));   // the scratch set is free again
+    } else if (pl->pipelined) {
+        int rc = plan_join(pl);    // a debug / partial launch on a pipelined plan: drain first, then run in order
+        if (rc) return rc;
+    }
+    const PlanDev P = plan_dev(pl, with_dbg, slot);
+    cudaStream_t s = sf;
     pl->last_launches = 0;
     CU(ctx, cudaMemsetAsync(pl->d_err, 0, 4, s));
-    CU(ctx, cudaEventRecord(pl->ev[0], s));
+    CU(ctx, cudaEventRecord(ev[0], s));
     if (pl->n_items && !pl->jit_on_host) {
         k_jitter_schedule<<<(pl->n_jscheds + 63) / 64, 64, 0, s>>>(P);
         pl->last_launches++;
     }
-    CU(ctx, cudaEventRecord(pl->ev[1], s));
+    CU(ctx, cudaEventRecord(ev[1], s));
     if (pl->n_items) {
         const uint32_t runs = (pl->chunk_len + FREQ_RUN - 1) / FREQ_RUN;
         const uint64_t threads = (uint64_t)pl->n_items * runs;
         k_frequency<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(P, runs);
         pl->last_launches++;
     }
-    CU(ctx, cudaEventRecord(pl->ev[2], s));
+    CU(ctx, cudaEventRecord(ev[2], s));
     for (size_t i = 0; i < pl->pscans.size(); ++i) {
         PScanDev S = pl->pscans[i];
         const uint32_t u = pl->pscan_utt[i];
-        S.F = pl->d_F + pl->utts[u].f_off;
+        S.F = P.F + pl->utts[u].f_off;
         S.status = pl->d_pscan_status + 16 * i;
         CU(ctx, cudaMemsetAsync(S.status, 0, 64, s));
         const uint32_t n = S.n, nb = (uint32_t)(((uint64_t)n + 1 + SCAN_TILE - 1) / SCAN_TILE);
@@ -631,12 +707,26 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
         k_phase_pair<<<(pl->n_utts + PH_UTTS - 1) / PH_UTTS, PH_UTTS * 64, 0, s>>>(P);
         pl->last_launches++;
     }
-    CU(ctx, cudaEventRecord(pl->ev[3], s));
+    CU(ctx, cudaEventRecord(ev[3], s));
+    if (pipe) {
+        CU(ctx, cudaEventRecord(pl->slot[slot].front_done, sf));
+        CU(ctx, cudaStreamWaitEvent(sb, pl->slot[slot].front_done, 0));
+        // ev[3] was recorded on the front stream; the formant kernel's own start is the later of that and the end of
+        // the previous formant kernel, so its launch time is measured between two events on the back stream
+        CU(ctx, cudaEventRecord(ev[3], sb));
+    }
+    s = sb;
     if (pl->n_items && formant) {
         launch_formant_of((int)pl->nw, (int)pl->fpt, P, d_out, format, s);
         pl->last_launches++;
     }
-    CU(ctx, cudaEventRecord(pl->ev[4], s));
+    CU(ctx, cudaEventRecord(ev[4], s));
+    if (pipe) {
+        CU(ctx, cudaEventRecord(pl->slot[slot].back_done, sb));
+        pl->slot[slot].used = true;
+        pl->in_flight = true;
+        pl->last_slot = (uint32_t)slot;
+    }
     CU(ctx, cudaGetLastError());
     pl->launched = true;
     return GRAIL_OK;
@@ -646,6 +736,8 @@ static int plan_check_device_errors(grail_plan* pl)
 {
     grail_ctx* ctx = pl->ctx;
     uint32_t e = 0;
+    int rcj = plan_join(pl);
+    if (rcj) return rcj;
     CU(ctx, cudaMemcpyAsync(&e, pl->d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (e & DEV_ERR_JIT_OVERFLOW) return set_err(ctx, GRAIL_ERR_CUDA, "device: jitter schedule overflow");
@@ -695,8 +787,12 @@ int grail_cuda_create(int device, grail_ctx** out_ctx)
     grail_ctx* ctx = new (std::nothrow) grail_ctx();
     if (!ctx) return GRAIL_ERR_OOM;
     ctx->device = device;
+    int prio_lo = 0, prio_hi = 0;
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->s_front, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->s_back, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
         cudaGetLastError();
         delete ctx;
         return GRAIL_ERR_CUDA;
@@ -716,6 +812,8 @@ void grail_cuda_destroy(grail_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->s_front) { cudaStreamSynchronize(ctx->s_front); cudaStreamDestroy(ctx->s_front); }
+    if (ctx->s_back) { cudaStreamSynchronize(ctx->s_back); cudaStreamDestroy(ctx->s_back); }
     for (auto& b : ctx->pool)
         if (b.ptr) cudaFree(b.ptr);
     for (int i = 0; i < 2; ++i) {
@@ -734,6 +832,8 @@ int grail_cuda_synchronize(grail_ctx* ctx)
 {
     if (!ctx) return GRAIL_ERR_INVALID_ARG;
     CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->s_front));
+    CU(ctx, cudaStreamSynchronize(ctx->s_back));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return GRAIL_OK;
 }
@@ -753,6 +853,8 @@ int grail_cuda_set_option(grail_ctx* ctx, const char* key, double value)
     } else if (!strcmp(key, "formants_per_lane")) {
         if (value != 1.0 && value != 2.0) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "formants_per_lane must be 1 or 2");
         ctx->formants_per_lane = (int)value;
+    } else if (!strcmp(key, "pipeline")) {
+        ctx->pipeline = value != 0.0;
     } else if (!strcmp(key, "pscan_min_samples")) {
         ctx->pscan_min = value < 1.0 ? 1u : (value > 4.0e9 ? 0xFFFFFFFFu : (uint32_t)value);
     } else if (!strcmp(key, "zero_copy_out")) {
@@ -804,13 +906,21 @@ int grail_cuda_plan_create(grail_ctx* ctx, const grail_seq_elem* elems, const ui
 {
     if (!ctx || !out_plan) return GRAIL_ERR_INVALID_ARG;
     *out_plan = nullptr;
-    return plan_build(ctx, elems, utt_offsets, voices, n_utts, out_plan);
+    return plan_build(ctx, elems, utt_offsets, voices, n_utts, out_plan, nullptr, true);
+}
+
+int grail_cuda_plan_join(grail_plan* plan)
+{
+    if (!plan) return GRAIL_ERR_INVALID_ARG;
+    return plan_join(plan);
 }
 
 void grail_cuda_plan_destroy(grail_plan* plan)
 {
     if (!plan) return;
     cudaSetDevice(plan->ctx->device);
+    cudaStreamSynchronize(plan->ctx->s_front);
+    cudaStreamSynchronize(plan->ctx->s_back);
     cudaStreamSynchronize(plan->ctx->stream);
     plan_release(plan);
 }
@@ -859,6 +969,8 @@ int grail_cuda_plan_read_output(grail_plan* plan, int format, void* host_out)
         return set_err(ctx, GRAIL_ERR_INVALID_ARG, "plan has no device output in this format; launch into "
                                                    "grail_cuda_plan_device_output first");
     const size_t bytes = (size_t)plan->total_samples * format_bytes(format);
+    int rcj = plan_join(plan);
+    if (rcj) return rcj;
     if (bytes) CU(ctx, cudaMemcpyAsync(host_out, plan->d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return plan_check_device_errors(plan);
 }
@@ -869,12 +981,20 @@ int grail_cuda_plan_timings(const grail_plan* plan, grail_timings* out)
     memset(out, 0, sizeof *out);
     if (!plan->launched) return GRAIL_OK;
     grail_ctx* ctx = plan->ctx;
-    CU(ctx, cudaEventSynchronize(plan->ev[4]));
-    CU(ctx, cudaEventElapsedTime(&out->schedule_ms, plan->ev[0], plan->ev[1]));
-    CU(ctx, cudaEventElapsedTime(&out->frequency_ms, plan->ev[1], plan->ev[2]));
-    CU(ctx, cudaEventElapsedTime(&out->phase_ms, plan->ev[2], plan->ev[3]));
-    CU(ctx, cudaEventElapsedTime(&out->formant_ms, plan->ev[3], plan->ev[4]));
-    CU(ctx, cudaEventElapsedTime(&out->total_ms, plan->ev[0], plan->ev[4]));
+    const bool piped = plan->pipelined && plan->slot[plan->last_slot].used;
+    const cudaEvent_t* ev = piped ? plan->slot[plan->last_slot].ev : plan->ev;
+    CU(ctx, cudaEventSynchronize(ev[4]));
+    CU(ctx, cudaEventElapsedTime(&out->schedule_ms, ev[0], ev[1]));
+    CU(ctx, cudaEventElapsedTime(&out->frequency_ms, ev[1], ev[2]));
+    if (piped) {   // ev[3] sits on the back stream there: phase = front-stream span minus the two kernels before it
+        float front = 0.f;
+        CU(ctx, cudaEventElapsedTime(&front, ev[2], ev[3]));
+        out->phase_ms = front;   // upper bound: includes waiting for the previous formant kernel
+    } else {
+        CU(ctx, cudaEventElapsedTime(&out->phase_ms, ev[2], ev[3]));
+    }
+    CU(ctx, cudaEventElapsedTime(&out->formant_ms, ev[3], ev[4]));
+    CU(ctx, cudaEventElapsedTime(&out->total_ms, ev[0], ev[4]));
     out->n_launches = plan->last_launches;
     return GRAIL_OK;
 }
@@ -886,6 +1006,8 @@ int grail_cuda_plan_phase_scan_stats(grail_plan* plan, uint32_t* stats)
     stats[0] = (uint32_t)plan->pscans.size();
     stats[1] = stats[2] = stats[3] = 0;
     if (plan->pscans.empty() || !plan->launched) return GRAIL_OK;
+    int rcj = plan_join(plan);
+    if (rcj) return rcj;
     std::vector<uint32_t> st(16 * plan->pscans.size());
     CU(ctx, cudaMemcpyAsync(st.data(), plan->d_pscan_status, st.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -928,7 +1050,7 @@ int grail_cuda_plan_read_intermediates(grail_plan* plan, float* frequency, float
     if (frequency && (rc = gather_linear(plan->d_F, frequency))) return rc;
     if (carrier_phase && (rc = gather_linear(plan->d_phase_dbg, carrier_phase))) return rc;
     if (saw) {
-        CU(ctx, cudaMemcpy(tmp.data(), plan->d_saw, plan->saw_words * sizeof(float), cudaMemcpyDeviceToHost));
+        CU(ctx, cudaMemcpy(tmp.data(), plan->slot[0].saw, plan->saw_words * sizeof(float), cudaMemcpyDeviceToHost));
         const uint32_t CL = plan->chunk_len;
         for (uint32_t u = 0; u < plan->n_utts; ++u) {
             const UttDev& U = plan->utts[u];

@@ -267,6 +267,10 @@ class Plan:
             d_out = self.device_output(fmt)
         self.ctx._check(self._L.grail_cuda_plan_launch(self._h, C.c_void_p(d_out), fmt))
 
+    def join(self):
+        """make the ctx's main stream wait (on the device) for this plan's in-flight launches"""
+        self.ctx._check(self._L.grail_cuda_plan_join(self._h))
+
     def read_output(self, out: Optional[np.ndarray] = None, fmt: int = _ffi.F32) -> np.ndarray:
         if out is None:
             out = np.empty(self.total_samples, np.float32 if fmt == _ffi.F32 else np.int16)

@@ -105,7 +105,9 @@ const char* grail_cuda_last_error(const grail_ctx* ctx);
 void* grail_cuda_stream_handle(grail_ctx* ctx);
 int  grail_cuda_synchronize(grail_ctx* ctx);
 /* tuning knobs: "warmup_nepers" (float, filter warm-up depth, default 13.8 ~ 1e-6),
- * "target_lanes" (int, time-chunks the planner aims for), "max_chunk" / "min_chunk" (samples) */
+ * "target_lanes" (int, time-chunks the planner aims for), "max_chunk" / "min_chunk" (samples),
+ * "formants_per_lane" (1|2), "pipeline" (0|1: overlap consecutive launches of a plan), "pscan_min_samples",
+ * "zero_copy_out" (0|1) */
 int  grail_cuda_set_option(grail_ctx* ctx, const char* key, double value);
 
 /* pinned host memory for full-rate H2D/D2H (optional; pageable buffers also work) */
@@ -139,6 +141,12 @@ int  grail_cuda_plan_out_offsets(const grail_plan* plan, uint64_t* out_offsets);
 /* enqueue every kernel of the path on the ctx stream; d_out is a DEVICE pointer to
  * total_samples elements of `format`.  Asynchronous: pair with grail_cuda_synchronize. */
 int  grail_cuda_plan_launch(grail_plan* plan, void* d_out, int format);
+/* With ctx option "pipeline" = 1 (off by default: measured no gain on B200, the latency-bound phase chains starve
+ * when they share SM sub-partitions with the formant kernel) launches of one plan are pipelined across the library's
+ * internal streams.  grail_cuda_plan_join makes the ctx's main stream (grail_cuda_stream_handle) wait, on the device,
+ * for everything the plan has in flight -- call it before recording an event or enqueueing a consumer on that stream
+ * (a no-op for unpipelined plans).  grail_cuda_synchronize, plan_read_output and plan_timings join implicitly. */
+int  grail_cuda_plan_join(grail_plan* plan);
 /* the plan's own device output buffer (allocated on first use), for callers with no allocator */
 int  grail_cuda_plan_device_output(grail_plan* plan, int format, void** out_dptr);
 /* D2H of the packed output into a host buffer (chunked, through pinned staging if pageable) */
