@@ -39,6 +39,9 @@ N_PHONEMES = 10
 # dominant kernel (k_formant) covers = everything but the scalar frequency/phase lane (26 flops)
 FLOPS_PER_SAMPLE = 762
 FLOPS_PER_SAMPLE_FORMANT = 736
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_formant launch on this workload, from the committed
+# `ncu --set full` capture (profiles/r1_k_formant_ncu_full.txt: 1.567 GB read + 0.868 GB written; algorithmic 1.806 GB)
+NCU_TRAFFIC_BYTES = 1566748000 + 867958528
 
 
 def host_cores() -> int:
@@ -259,10 +262,14 @@ def run_ours(args):
         hbm_bytes = 4 * n_samples * 2          # saw read + f32 samples written (algorithmic bytes of k_formant)
         roofline = {
             "kernel": "k_formant", "bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": achieved_tf / peak_tf, "traffic": None,
+            "frac": achieved_tf / peak_tf, "traffic": NCU_TRAFFIC_BYTES,
             "peak_source": "FFMA issue-rate probe measured live in this run (MEASURED_PEAKS.json has no fp32 figure)",
             "flops_per_sample": FLOPS_PER_SAMPLE_FORMANT, "launch_ms": formant_ms,
-            "mufu_rcp_per_s": 3 * 4 * n_samples / (formant_ms * 1e-3), "mufu_peak_per_s": probe["mufu_ops"],
+            "note": "achieved counts the reference's as-written flops (SURVEY 8d); the kernel executes fewer: 4 of the "
+                    "8 formants of the default voice are exactly zero and are skipped, and the 7 per-sample filter "
+                    "coefficients are interpolated between exact 8-sample end points, so frac can exceed 1; ncu "
+                    "(profiles/r1_k_formant_ncu_full.txt) reads 64 % issue-slot utilisation",
+            "mufu_peak_per_s": probe["mufu_ops"],
             "hbm": {"achieved": hbm_bytes / (formant_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                     "frac": (hbm_bytes / (formant_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
                     "peak_source": "MEASURED_PEAKS.json (measured)" if peaks.get("hbm_gbs") else "absent"},
