@@ -427,10 +427,11 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
         const bool lane0 = lane == 0;
         for (uint32_t tile = 0; tile < ntiles; ++tile) {
             const int buf = tile & 1;
-            issue(tile + PH_AHEAD);             // stage (tile-2) % 8: released by the saw warp two tiles ago
+            // the saw warp has consumed tile-2: its phase buffer AND its F stage (the one refilled next) are free
+            mbar_wait(empty_a + buf * 8, ((tile >> 1) & 1) ^ 1);   // first use of each buffer passes at once
+            issue(tile + PH_AHEAD);             // into stage (tile-2) % 8
             cp_async_wait<PH_AHEAD>();
             __syncwarp();
-            mbar_wait(empty_a + buf * 8, ((tile >> 1) & 1) ^ 1);   // first use of each buffer passes at once
             const unsigned fa_ = sF_a + (tile % PH_STAGES) * (PH_TILE * 4);   // this tile's F_t
             const unsigned pa_ = sP_a + buf * (32 * 4);                        // block-start phases out
             const uint32_t odd = lds32u(sG_a + (tile % PH_STAGES) * 8) | lds32u(sG_a + (tile % PH_STAGES) * 8 + 4);

@@ -1,0 +1,26 @@
+"""small end-to-end run for compute-sanitizer (memcheck / racecheck): batch with chunking, long-form scan, stream"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import grail_rs_b200 as g
+from grail_rs_b200 import workloads as W
+ctx = g.Context(0)
+ctx.set_option("min_chunk", 1024); ctx.set_option("target_lanes", 1 << 20)
+elems, offs, vp = W.from_phonemes([[0, 4, 3], [3], [0, 0, 4, 3]], g.voices.generic(), [1, 2, 3])
+elems = elems.copy(); elems["length"] = 0.05
+out, oo = ctx.synthesize_batch(elems, offs, vp)
+print("batch", len(out), float(np.abs(out).sum()))
+ctx.set_option("pscan_min_samples", 1)
+out2, _ = ctx.synthesize_batch(elems, offs, vp)
+print("pscan", float(np.abs(out2 - out).max()))
+e4, o4, v4 = W.config4(3, first_utt=7)
+e4 = e4.copy(); e4["length"] = 0.04
+out4, _ = ctx.synthesize_batch(e4, o4, v4)
+print("cfg4", len(out4))
+st = ctx.stream(vp[0]); st.push(elems[:3]); st.finish()
+n = 0
+while True:
+    x = st.pull(777)
+    if len(x) == 0: break
+    n += len(x)
+print("stream", n)

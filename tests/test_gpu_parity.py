@@ -219,3 +219,36 @@ def test_full_size_config2_properties(ctx, oracle):
         assert st["max_abs"] <= MAX_ABS and st["snr_db"] >= MIN_SNR_DB, (u, st)
     print(plan.timings())
     plan.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_randomized_batches(ctx, oracle, seed):
+    """random phoneme lists (incl. Stop/Glide), ragged random lengths and blend lengths, mixed sample rates and
+    random-voice elements in one batch, random jitter seeds and chunkings"""
+    rng = np.random.default_rng(seed)
+    v441 = g.voices.generic()
+    parts, offs, vps = [], [0], []
+    for u in range(10):
+        rate = float(rng.choice([16000.0, 22050.0, 44100.0, 48000.0]))
+        if rng.random() < 0.4:
+            e, o, vp = W.config4(1, sample_rate=rate, first_utt=int(rng.integers(0, 60000)))
+            e = e.copy()
+        else:
+            voice = v441 if rate == 44100.0 else g.voices.at_sample_rate(v441, rate)
+            n = int(rng.integers(1, 6))
+            e, o, vp = W.from_phonemes([[int(x) for x in rng.integers(0, 5, n)]], voice, [int(rng.integers(0, 2**32))])
+            e = e.copy()
+        e["length"] = rng.uniform(0.03, 0.6, len(e)).astype(np.float32)
+        e["blend_length"] = np.where(rng.random(len(e)) < 0.5, e["length"], rng.uniform(0.01, 0.7, len(e))).astype(np.float32)
+        parts.append(e)
+        offs.append(offs[-1] + len(e))
+        vps.append(vp[0])
+    elems = np.concatenate(parts)
+    ctx.set_option("min_chunk", int(rng.choice([256, 1024, 2048, 8192])))
+    ctx.set_option("target_lanes", int(rng.choice([0, 1 << 20, 64])))
+    try:
+        worst, _, _ = check_batch(ctx, oracle, elems, np.array(offs, np.uint32), np.array(vps), label=f"rand{seed}")
+        print(worst)
+    finally:
+        ctx.set_option("min_chunk", 2048)
+        ctx.set_option("target_lanes", 0)
