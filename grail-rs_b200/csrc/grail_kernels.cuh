@@ -1108,15 +1108,19 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
 
     // Per-sample coefficients of one formant at clock values (alpha, jph): the Sequencer blend (:404-414), the
     // Jitter perturbation (:764-773), exp_approx (:75-82) and the SVF coefficients (:555-562).
-    struct Coef { float a1, a2, a3, lp, amp, br, tb; };   // lp = 1 - exp_approx(smooth)
+    // lp = 1 - exp_approx(smooth); turbulence and amplitude are folded: v0 = a * (amp0 + amp1 * noise) with
+    // amp0 = amp (1 - turb), amp1 = amp turb   (1 * (1 - turb) + noise * turb, times amp: :544-550)
+    struct Coef { float a1, a2, a3, lp, amp0, amp1, br; };
     auto coeffs = [&](const FormantLane& F, float alpha, float jp) -> Coef {
         Coef c;
         const float ff = fmaf(jp, F.ff2, fmaf(alpha, F.ff1, F.ff0));
         const float bw = fmaf(alpha, F.bw1, F.bw0);
         const float o = fmaf(alpha, F.om1, F.om0);                            // 1 - smooth
         c.br = fmaf(alpha, F.br1, F.br0);
-        c.tb = fmaf(alpha, F.tb1, F.tb0);
-        c.amp = fmaf(alpha, F.am1, F.am0) * fmaf(jp, F.aj1, F.aj0);
+        const float tb = fmaf(alpha, F.tb1, F.tb0);
+        const float amp = fmaf(alpha, F.am1, F.am0) * fmaf(jp, F.aj1, F.aj0);
+        c.amp1 = amp * tb;
+        c.amp0 = amp - c.amp1;
         const float o2 = o * o;
         c.lp = fmaf(-o2 * o2, o, 1.0f);
         float num, den;
@@ -1129,10 +1133,10 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
         return c;
     };
     // One filter step of one formant (:531-571): breath mix, one-pole low-pass, turbulence, amplitude, SVF tick.
-    auto tick = [&](FormantLane& F, const Coef& c, float saw, float d1, float nzm1) -> float {
+    auto tick = [&](FormantLane& F, const Coef& c, float saw, float d1, float nz) -> float {
         const float nw = fmaf(c.br, d1, saw);                                 // :531
         F.a = fmaf(c.lp, nw - F.a, F.a);                                      // :538
-        const float v0 = F.a * fmaf(c.tb, nzm1, 1.0f) * c.amp;                // :544-550
+        const float v0 = F.a * fmaf(c.amp1, nz, c.amp0);                      // :544-550
         const float v3 = v0 - F.c;                                            // :565
         const float v1 = fmaf(c.a1, F.b, c.a2 * v3);
         const float v2 = fmaf(c.a3, v3, fmaf(c.a2, F.b, F.c));
@@ -1141,20 +1145,19 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
         return v1;
     };
     // aspiration noise of the next sample (:528) and the two differences every formant uses
-    auto noise = [&](float saw, float& d1, float& nzm1) {
+    auto noise = [&](float saw, float& d1, float& nz) {
         s_noise = s_noise * LCG_A + LCG_C;                                    // :40
-        const float nz = fmaf(__uint_as_float((s_noise >> 9) | 0x3F800000u), 2.0f, -3.0f);
+        nz = fmaf(__uint_as_float((s_noise >> 9) | 0x3F800000u), 2.0f, -3.0f);
         d1 = nz - saw;
-        nzm1 = nz - 1.0f;
     };
     // one sample with exact per-sample coefficients: all formants of this lane; returns their v1 sum (:566)
     auto sample = [&](float saw) -> float {
         const float alpha = fminf(time * inv_bl, 1.0f);                       // :899
-        float d1, nzm1;
-        noise(saw, d1, nzm1);
+        float d1, nz;
+        noise(saw, d1, nz);
         float acc = 0.0f;
 #pragma unroll
-        for (int j = 0; j < FPT; ++j) acc += tick(L[j], coeffs(L[j], alpha, jph), saw, d1, nzm1);
+        for (int j = 0; j < FPT; ++j) acc += tick(L[j], coeffs(L[j], alpha, jph), saw, d1, nz);
         return acc;
     };
 
@@ -1261,24 +1264,24 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
                         c0[j] = cend[j];
                         cend[j] = coeffs(L[j], alpha, jph);
                         dc[j].a1 = cend[j].a1 - c0[j].a1; dc[j].a2 = cend[j].a2 - c0[j].a2; dc[j].a3 = cend[j].a3 - c0[j].a3;
-                        dc[j].lp = cend[j].lp - c0[j].lp; dc[j].amp = cend[j].amp - c0[j].amp;
-                        dc[j].br = cend[j].br - c0[j].br; dc[j].tb = cend[j].tb - c0[j].tb;
+                        dc[j].lp = cend[j].lp - c0[j].lp; dc[j].amp0 = cend[j].amp0 - c0[j].amp0;
+                        dc[j].amp1 = cend[j].amp1 - c0[j].amp1; dc[j].br = cend[j].br - c0[j].br;
                     }
                 }
                 c_valid = true;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    float d1, nzm1;
-                    noise(s8[k], d1, nzm1);
+                    float d1, nz;
+                    noise(s8[k], d1, nz);
                     const float t = (float)k * 0.125f;
                     float acc = 0.0f;
 #pragma unroll
                     for (int j = 0; j < FPT; ++j) {
                         Coef c;
                         c.a1 = fmaf(dc[j].a1, t, c0[j].a1); c.a2 = fmaf(dc[j].a2, t, c0[j].a2); c.a3 = fmaf(dc[j].a3, t, c0[j].a3);
-                        c.lp = fmaf(dc[j].lp, t, c0[j].lp); c.amp = fmaf(dc[j].amp, t, c0[j].amp);
-                        c.br = fmaf(dc[j].br, t, c0[j].br); c.tb = fmaf(dc[j].tb, t, c0[j].tb);
-                        acc += tick(L[j], c, s8[k], d1, nzm1);
+                        c.lp = fmaf(dc[j].lp, t, c0[j].lp); c.amp0 = fmaf(dc[j].amp0, t, c0[j].amp0);
+                        c.amp1 = fmaf(dc[j].amp1, t, c0[j].amp1); c.br = fmaf(dc[j].br, t, c0[j].br);
+                        acc += tick(L[j], c, s8[k], d1, nz);
                     }
                     v[k] = acc;
                 }
