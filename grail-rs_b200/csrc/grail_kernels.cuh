@@ -1347,7 +1347,7 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
                         const uint32_t cnt = min(4u, rl - s0);
                         if (format == GRAIL_F32) {
                             float* op = reinterpret_cast<float*>(out) + o;
-                            if (cnt == 4 && (o & 3ull) == 0) {
+                            if (cnt == 4 && (reinterpret_cast<uintptr_t>(op) & 15u) == 0) {   // 128-bit store when the row is 16-byte aligned
                                 *reinterpret_cast<float4*>(op) = acc;
                             } else {
                                 const float a4[4] = { acc.x, acc.y, acc.z, acc.w };

@@ -252,3 +252,21 @@ def test_randomized_batches(ctx, oracle, seed):
     finally:
         ctx.set_option("min_chunk", 2048)
         ctx.set_option("target_lanes", 0)
+
+
+def test_unaligned_device_output(ctx, oracle):
+    """a caller-provided device buffer that is only 4-byte aligned (the kernel's 128-bit stores must fall back)"""
+    import torch
+    elems, offs, vp = W.from_phonemes([[0, 3], [4]], g.voices.generic(), [1, 2])
+    plan = ctx.plan(elems, offs, vp)
+    buf = torch.zeros(plan.total_samples + 8, dtype=torch.float32, device="cuda")
+    for shift in (1, 2, 3):
+        plan.launch(buf.data_ptr() + 4 * shift)
+        ctx.synchronize()
+        got = buf[shift:shift + plan.total_samples].cpu().numpy()
+        oo = plan.out_offsets
+        for u in range(2):
+            want, _, _ = oracle.synthesize(elems[offs[u]:offs[u + 1]], vp[u])
+            st = W.parity_stats(got[oo[u]:oo[u + 1]], want)
+            assert st["max_abs"] <= MAX_ABS and st["snr_db"] >= MIN_SNR_DB, (shift, u, st)
+    plan.close()
