@@ -471,6 +471,13 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
             const int cta_regs = std::max(1, 65536 / occ);
             const int reserve = (32768 + cta_regs - 1) / cta_regs;
             occ = std::max(occ - reserve, (occ + 1) / 2);
+        } else {
+            // Fewer, longer chunks beat full occupancy (the warm-up is paid per chunk): aim at ~3/4 of the resident
+            // CTAs, and keep the warps per SM a multiple of 4 so the four sub-partitions stay evenly loaded
+            // (measured at config 2, FPT = 2: 6 CTAs/SM 2.13 ms, 8 -> 2.23 ms, 5 / 7 -> 2.37 / 2.40 ms).
+            int c = std::max(1, (3 * occ) / 4);
+            while (c > 1 && ((c * (int)nw) % 4) != 0) --c;
+            occ = c;
         }
         target = (uint64_t)ctx->prop.multiProcessorCount * (uint64_t)occ * 32ull;
     }
