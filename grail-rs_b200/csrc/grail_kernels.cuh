@@ -485,6 +485,9 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
         // ---------------- saw warp ----------------
         float* dbg = P.phase_dbg ? P.phase_dbg + U.f_off : nullptr;
         const uint32_t CL = P.chunk_len;
+        // destination of this lane's 32-byte sector: tiles advance 256 samples and CL is a multiple of 256, so the
+        // (chunk, offset) pair is tracked incrementally instead of divided out every tile
+        uint32_t dst_item = U.item_first, dst_j = lane * 8;
         for (uint32_t tile = 0; tile < ntiles; ++tile) {
             const int buf = tile & 1;
             mbar_wait(full_a + buf * 8, (tile >> 1) & 1);
@@ -511,13 +514,12 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
                 }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    s[k] = ssub(smul(2.0f, pv[k]), 1.0f);                               // :517 with polyblep = 0
+                    s[k] = fmaf(2.0f, pv[k], -1.0f);                                    // :517 with polyblep = 0 (2p is exact)
                     const bool edge = !((pv[k] >= fv[k]) && (pv[k] <= ssub(1.0f, fv[k])));
                     if (edge) s[k] = saw_edge(pv[k], fv[k]);
                     if ((uint32_t)k >= valid) s[k] = 0.0f;
                 }
-                const uint32_t item = U.item_first + b0 / CL, j = b0 % CL;
-                float4* dst = reinterpret_cast<float4*>(P.saw + saw_index(item, j, CL));
+                float4* dst = reinterpret_cast<float4*>(P.saw + saw_index(dst_item, dst_j, CL));
                 dst[0] = make_float4(s[0], s[1], s[2], s[3]);
                 dst[1] = make_float4(s[4], s[5], s[6], s[7]);
                 if (dbg) {
@@ -526,6 +528,8 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
                         if ((uint32_t)k < valid) dbg[b0 + k] = pv[k];
                 }
             }
+            dst_j += PH_TILE;
+            if (dst_j >= CL) { dst_j -= CL; ++dst_item; }
         }
     }
 }
