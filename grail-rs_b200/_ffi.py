@@ -47,7 +47,7 @@ EXPORTS = [
     "grail_cuda_destroy", "grail_cuda_last_error", "grail_cuda_stream_handle", "grail_cuda_synchronize",
     "grail_cuda_set_option", "grail_cuda_host_alloc", "grail_cuda_host_free", "grail_cuda_count_samples",
     "grail_cuda_synthesize_batch", "grail_cuda_plan_create", "grail_cuda_plan_destroy",
-    "grail_cuda_plan_join", "grail_cuda_plan_total_samples", "grail_cuda_plan_out_offsets", "grail_cuda_plan_launch",
+    "grail_cuda_plan_join", "grail_cuda_plan_total_samples", "grail_cuda_plan_out_offsets", "grail_cuda_plan_launch", "grail_cuda_plan_launch_interleaved",
     "grail_cuda_plan_device_output", "grail_cuda_plan_read_output", "grail_cuda_plan_timings",
     "grail_cuda_plan_read_intermediates", "grail_cuda_plan_phase_scan_stats", "grail_cuda_stream_new", "grail_cuda_stream_push",
     "grail_cuda_stream_finish", "grail_cuda_stream_pull", "grail_cuda_stream_free", "grail_cuda_probe_fp32_peak",
@@ -85,6 +85,7 @@ def lib() -> C.CDLL:
         "grail_cuda_plan_total_samples": (u64, [vp]),
         "grail_cuda_plan_out_offsets": (i32, [vp, vp]),
         "grail_cuda_plan_launch": (i32, [vp, vp, i32]),
+        "grail_cuda_plan_launch_interleaved": (i32, [vp, vp, i32, u32]),
         "grail_cuda_plan_device_output": (i32, [vp, i32, C.POINTER(vp)]),
         "grail_cuda_plan_read_output": (i32, [vp, i32, vp]),
         "grail_cuda_plan_timings": (i32, [vp, C.POINTER(Timings)]),

@@ -76,6 +76,7 @@ struct PlanDev {
     uint32_t*           err;       // device error word
     uint32_t n_utts, n_items, n_groups, n_jscheds;
     uint32_t chunk_len;            // CL, multiple of 256
+    uint32_t out_channels;         // every sample is written this many times, interleaved (examples/cli.rs:229)
     float    warmup_nepers;
 };
 
@@ -1349,12 +1350,24 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
                         acc.x *= 0.5f; acc.y *= 0.5f; acc.z *= 0.5f; acc.w *= 0.5f;
                         const unsigned long long o = row_out[row] + s0;
                         const uint32_t cnt = min(4u, rl - s0);
-                        if (format == GRAIL_F32) {
+                        const float a4[4] = { acc.x, acc.y, acc.z, acc.w };
+                        const uint32_t nch = P.out_channels;
+                        if (nch != 1u) {
+                            // channel duplication, `flat_map(|x| repeat(x).take(num_channels))` (examples/cli.rs:229,
+                            // interactive.rs:38): each sample nch times, interleaved
+                            for (uint32_t q = 0; q < cnt; ++q) {
+                                const float sc = a4[q] * 32767.0f;
+                                const short qi = (short)((sc != sc) ? 0 : __float2int_rz(fminf(fmaxf(sc, -32768.0f), 32767.0f)));
+                                for (uint32_t c = 0; c < nch; ++c) {
+                                    if (format == GRAIL_F32) reinterpret_cast<float*>(out)[(o + q) * nch + c] = a4[q];
+                                    else reinterpret_cast<short*>(out)[(o + q) * nch + c] = qi;
+                                }
+                            }
+                        } else if (format == GRAIL_F32) {
                             float* op = reinterpret_cast<float*>(out) + o;
                             if (cnt == 4 && (reinterpret_cast<uintptr_t>(op) & 15u) == 0) {   // 128-bit store when the row is 16-byte aligned
                                 *reinterpret_cast<float4*>(op) = acc;
                             } else {
-                                const float a4[4] = { acc.x, acc.y, acc.z, acc.w };
 #pragma unroll
                                 for (int q = 0; q < 4; ++q)
                                     if ((uint32_t)q < cnt) op[q] = a4[q];
@@ -1362,7 +1375,6 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
                         } else {
                             // (x * i16::MAX as f32) as i16: truncating, saturating, NaN -> 0 (examples/cli.rs:50)
                             short* op = reinterpret_cast<short*>(out) + o;
-                            const float a4[4] = { acc.x, acc.y, acc.z, acc.w };
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 const float sc = a4[q] * 32767.0f;

@@ -143,6 +143,7 @@ struct grail_plan {
         cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
         bool used = false;
     } slot[2];
+    uint32_t out_channels = 1;
     bool pipelined = false, in_flight = false;
     uint32_t launch_idx = 0, last_slot = 0;
     cudaEvent_t ev_begin = nullptr;
@@ -321,6 +322,7 @@ static PlanDev plan_dev(const grail_plan* pl, bool with_dbg, int slot = 0)
     P.utt_final = pl->d_utt_final;
     P.n_utts = pl->n_utts; P.n_items = pl->n_items; P.n_groups = pl->n_groups; P.n_jscheds = pl->n_jscheds;
     P.chunk_len = pl->chunk_len;
+    P.out_channels = pl->out_channels;
     P.warmup_nepers = (float)pl->ctx->warmup_nepers;
     return P;
 }
@@ -945,7 +947,19 @@ int grail_cuda_plan_launch(grail_plan* plan, void* d_out, int format)
 {
     if (!plan) return GRAIL_ERR_INVALID_ARG;
     if (!d_out && plan->total_samples) return set_err(plan->ctx, GRAIL_ERR_INVALID_ARG, "null output pointer");
+    plan->out_channels = 1;
     return plan_enqueue(plan, d_out, format, false, true);
+}
+
+int grail_cuda_plan_launch_interleaved(grail_plan* plan, void* d_out, int format, uint32_t channels)
+{
+    if (!plan) return GRAIL_ERR_INVALID_ARG;
+    if (channels < 1 || channels > 32) return set_err(plan->ctx, GRAIL_ERR_INVALID_ARG, "channels must be 1..32");
+    if (!d_out && plan->total_samples) return set_err(plan->ctx, GRAIL_ERR_INVALID_ARG, "null output pointer");
+    plan->out_channels = channels;
+    const int rc = plan_enqueue(plan, d_out, format, false, true);
+    plan->out_channels = 1;
+    return rc;
 }
 
 int grail_cuda_plan_device_output(grail_plan* plan, int format, void** out_dptr)

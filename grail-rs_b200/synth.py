@@ -267,6 +267,10 @@ class Plan:
             d_out = self.device_output(fmt)
         self.ctx._check(self._L.grail_cuda_plan_launch(self._h, C.c_void_p(d_out), fmt))
 
+    def launch_interleaved(self, d_out: int, channels: int, fmt: int = _ffi.F32):
+        """every sample written `channels` times, interleaved (the examples' channel duplication) into a caller buffer"""
+        self.ctx._check(self._L.grail_cuda_plan_launch_interleaved(self._h, C.c_void_p(d_out), fmt, channels))
+
     def join(self):
         """make the ctx's main stream wait (on the device) for this plan's in-flight launches"""
         self.ctx._check(self._L.grail_cuda_plan_join(self._h))
@@ -328,6 +332,18 @@ class Stream:
             self._h = None
 
     __del__ = close
+
+
+def save_wav(path: str, data: np.ndarray, sample_rate: int, channels: int = 1) -> None:
+    """16-bit PCM RIFF writer of examples/cli.rs:28-67; `data` is f32 (converted like the reference,
+    `(x * i16::MAX as f32) as i16`) or already int16 (GRAIL_I16 device output)"""
+    import struct
+    pcm = data if data.dtype == np.int16 else np.clip(np.trunc(np.nan_to_num(data.astype(np.float32)) * np.float32(32767.0)), -32768, 32767).astype(np.int16)
+    raw = pcm.astype("<i2").tobytes()
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + len(raw)) + b"WAVE" + b"fmt " +
+                struct.pack("<IHHIIHH", 16, 1, channels, sample_rate, sample_rate * 2 * channels, 2 * channels, 16) +
+                b"data" + struct.pack("<I", len(raw)) + raw)
 
 
 def count_samples(elems: np.ndarray, utt_offsets: np.ndarray, voices: np.ndarray) -> np.ndarray:

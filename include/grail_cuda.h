@@ -141,6 +141,10 @@ int  grail_cuda_plan_out_offsets(const grail_plan* plan, uint64_t* out_offsets);
 /* enqueue every kernel of the path on the ctx stream; d_out is a DEVICE pointer to
  * total_samples elements of `format`.  Asynchronous: pair with grail_cuda_synchronize. */
 int  grail_cuda_plan_launch(grail_plan* plan, void* d_out, int format);
+/* The same with every sample written `channels` times, interleaved: the examples' channel duplication
+ * `flat_map(|x| repeat(x).take(num_channels))` (examples/cli.rs:229, interactive.rs:38) done on the device.
+ * d_out holds total_samples * channels elements; utterance u starts at out_offsets[u] * channels. */
+int  grail_cuda_plan_launch_interleaved(grail_plan* plan, void* d_out, int format, uint32_t channels);
 /* With ctx option "pipeline" = 1 (off by default: measured no gain on B200, the latency-bound phase chains starve
  * when they share SM sub-partitions with the formant kernel) launches of one plan are pipelined across the library's
  * internal streams.  grail_cuda_plan_join makes the ctx's main stream (grail_cuda_stream_handle) wait, on the device,

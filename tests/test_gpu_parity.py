@@ -270,3 +270,54 @@ def test_unaligned_device_output(ctx, oracle):
             st = W.parity_stats(got[oo[u]:oo[u + 1]], want)
             assert st["max_abs"] <= MAX_ABS and st["snr_db"] >= MIN_SNR_DB, (shift, u, st)
     plan.close()
+
+
+def test_interleaved_channels_and_wav(ctx, oracle, tmp_path):
+    """f2 of SURVEY 8f: channel duplication (examples/cli.rs:229) and 16-bit PCM on the device, RIFF header on the host"""
+    import torch
+    elems, offs, vp = W.from_phonemes([[0, 3, 4], [4]], g.voices.generic(), [5, 6])
+    plan = ctx.plan(elems, offs, vp)
+    plan.launch()
+    mono = plan.read_output().copy()
+    for ch in (2, 3):
+        buf = torch.zeros(plan.total_samples * ch, dtype=torch.float32, device="cuda")
+        plan.launch_interleaved(buf.data_ptr(), ch)
+        ctx.synchronize()
+        got = buf.cpu().numpy().reshape(-1, ch)
+        assert np.array_equal(got[:, 0].view(np.uint32), mono.view(np.uint32))
+        assert all(np.array_equal(got[:, 0], got[:, c]) for c in range(1, ch))
+    pcm = torch.zeros(plan.total_samples * 2, dtype=torch.int16, device="cuda")
+    plan.launch_interleaved(pcm.data_ptr(), 2, fmt=g.I16)
+    ctx.synchronize()
+    pcm = pcm.cpu().numpy()
+    ref = np.trunc(mono * np.float32(32767.0)).astype(np.int16)
+    assert np.array_equal(pcm[0::2], ref) and np.array_equal(pcm[1::2], ref)
+    path = str(tmp_path / "out.wav")
+    g.save_wav(path, pcm, 44100, channels=2)
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"RIFF" and raw[8:16] == b"WAVEfmt " and len(raw) == 44 + 2 * len(pcm)
+    plan.close()
+
+
+def test_synthesize_resampled_property(ctx, oracle):
+    """the author's empty `synthesize_resampled` (src/lib.rs:606-608): resampling gives a similar output.
+    Same phonemes at 44.1 kHz and 22.05 kHz: same duration, similar level, similar spectral envelope."""
+    ph = [[0, 3, 4, 3]]
+    v = g.voices.generic()
+    outs = {}
+    for rate in (44100.0, 22050.0):
+        voice = v if rate == 44100.0 else g.voices.at_sample_rate(v, rate)
+        e, o, p = W.from_phonemes(ph, voice, [3])
+        outs[rate], _ = ctx.synthesize_batch(e, o, p)
+    a, b = outs[44100.0], outs[22050.0]
+    assert abs(len(a) / 44100.0 - len(b) / 22050.0) < 1e-3
+    ra, rb = np.sqrt(np.mean(a.astype(np.float64) ** 2)), np.sqrt(np.mean(b.astype(np.float64) ** 2))
+    assert 0.5 < ra / rb < 2.0
+    # band energies below 5 kHz on a common frequency grid
+    def bands(x, rate):
+        spec = np.abs(np.fft.rfft(x.astype(np.float64) * np.hanning(len(x)))) ** 2
+        freqs = np.fft.rfftfreq(len(x), 1.0 / rate)
+        edges = np.linspace(100, 5000, 15)
+        e = np.array([spec[(freqs >= lo) & (freqs < hi)].sum() for lo, hi in zip(edges[:-1], edges[1:])])
+        return np.log10(e / e.sum())
+    assert np.abs(bands(a, 44100.0) - bands(b, 22050.0)).max() < 1.0      # within a decade in every band
