@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
 //             that start in it), giving the rounded increments; an exact integer prefix sum of them is the new P~
 //   stop      when a fully parallel check with REAL f32 ops, step(P_t, F_t) == P_{t+1} for every t, passes:
 //             by induction from P_0 the trajectory is then the reference's, bit for bit.
-// Converges in 3-5 rounds (measured); if it has not after PS_MAX_ROUNDS, or some F_t is outside [2^-16, 0.5],
+// Converges in 1-5 rounds (measured); if it has not after PS_MAX_ROUNDS, or some F_t is outside [2^-16, 0.5],
 // the done flag stays 0 and k_phase_pair runs the serial chain for that utterance instead.
 // ------------------------------------------------------------------------------------------------
 constexpr int PS_MAX_ROUNDS = 12;
@@ -564,6 +564,7 @@ struct PScanDev {
     unsigned long long* P;          // n + 1 fixed-point phases (estimate, then result)
     unsigned long long* inc;        // n rounded increments
     unsigned long long* bsum;       // scan spine
+    unsigned char* cls;             // per step, from the current estimate: grid exponent g (bits 0-4), wraps (bit 5)
     unsigned char* sflag;           // per step: bit0 parity of the carry into the high part, bit1 tie on a wrap step, bit2 parity of c at the tie
     unsigned char* bpar;            // per 256-step block: parity transducer (bit1 has_tie, bit0 xor), then incoming parity
     uint32_t* status;               // {mismatches, done, rounds, unsupported}
@@ -647,15 +648,20 @@ __global__ void __launch_bounds__(1024) k_ps_scan_spine(PScanDev S, uint32_t nb)
         __syncthreads();
     }
 }
-__global__ void __launch_bounds__(SCAN_THREADS) k_ps_scan_apply(PScanDev S)
+// Third scan pass, fused with what every step needs from the new estimate: (a) the proof -- the step redone with
+// real f32 operations must land on the next phase (counted into status[0] when `verify`), and (b) the step's class
+// for the next round's replay: rounding grid and "reaches 1.0".
+__global__ void __launch_bounds__(SCAN_THREADS) k_ps_scan_apply(PScanDev S, int verify)
 {
     if (S.status[1] | S.status[3]) return;
     __shared__ unsigned long long sh[SCAN_THREADS / 32];
     const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     unsigned long long v[SCAN_ITEMS], s = 0;
+    float f[SCAN_ITEMS];
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
         v[i] = (base + i < S.n) ? S.inc[base + i] : 0ull;
+        f[i] = (base + i < S.n) ? __ldg(S.F + base + i) : 0.25f;
         s += v[i];
     }
     unsigned long long x = s;
@@ -669,88 +675,121 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_ps_scan_apply(PScanDev S)
     unsigned long long woff = 0;
     for (int i = 0; i < (int)(threadIdx.x >> 5); ++i) woff += sh[i];
     unsigned long long run = S.p0 + S.bsum[blockIdx.x] + woff + (x - s);   // exclusive prefix of this lane's first item
+    unsigned bad = 0;
+    unsigned long long cpack = 0;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
-        if (base + i <= S.n) S.P[base + i] = run & PS_MASK;                // P[n] (the final phase) included
+        const unsigned long long p = run & PS_MASK;
+        if (base + i <= S.n) S.P[base + i] = p;                            // P[n] (the final phase) included
         run += v[i];
+        if (base + i < S.n) {
+            const unsigned long long q = run & PS_MASK;
+            const float a = __ull2float_rn(p) * 9.094947017729282e-13f;    // * 2^-40
+            const float c = __ull2float_rn(q) * 9.094947017729282e-13f;
+            bool b = ((unsigned long long)(a * 1099511627776.0f) != p) || ((unsigned long long)(c * 1099511627776.0f) != q);
+            float nx = sadd(a, f[i]);                                      // :520
+            if (nx >= 1.0f) nx = ssub(nx, 1.0f);                           // :523-525
+            b |= __float_as_uint(nx) != __float_as_uint(c);
+            bad += b ? 1u : 0u;
+            const unsigned long long xx = p + ps_fix(f[i]);
+            const int g = ps_grid(xx);
+            cpack |= (unsigned long long)(unsigned)(g | ((ps_rhe(xx, g, -1) >= PS_ONE) ? 32 : 0)) << (8 * i);
+        }
+    }
+    static_assert(SCAN_ITEMS == 8, "class bytes are packed into one 8-byte store");
+    if (base + SCAN_ITEMS <= S.n) {
+        *reinterpret_cast<unsigned long long*>(S.cls + base) = cpack;
+    } else {
+        for (int i = 0; i < SCAN_ITEMS; ++i)
+            if (base + i < S.n) S.cls[base + i] = (unsigned char)(cpack >> (8 * i));
+    }
+    if (verify) {
+        const unsigned m = __reduce_add_sync(0xffffffffu, bad);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(S.status, m);
     }
 }
 
 // One lane per 256-sample block.  The low bits L restart from 0 after every wrap, so the lane first looks BACK for
 // the last step before its block that wraps under the current estimate (a whole carrier period at most), replays
 // forward from there without writing, and then replays its own block writing the rounded increments and the
-// parity flags.  Grids, wraps and tie flags are classified from the estimate P~.
+// parity flags.  Grids and wraps come from k_ps_classify.
 constexpr uint32_t PS_MAX_LOOKBACK = 1u << 16;
 
 __global__ void __launch_bounds__(128) k_ps_replay(PScanDev S)
 {
-    if (S.status[1] | S.status[3]) return;
+    if (S.status[1] | S.status[3]) return;                       // uniform over the grid
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t t0_ = (uint64_t)b * PS_BLOCK;
-    if (t0_ >= S.n) return;
-    const uint32_t t0 = (uint32_t)t0_;
-    const uint32_t t1 = (uint32_t)min((uint64_t)S.n, t0_ + PS_BLOCK);
-    // step s under the current estimate: exact-sum estimate x, its grid, and whether it reaches 1.0
-    auto classify = [&](uint32_t s, unsigned long long& fi, int& g) -> bool {
-        fi = ps_fix(__ldg(S.F + s));
-        const unsigned long long x = S.P[s] + fi;
-        g = ps_grid(x);
-        return ps_rhe(x, g, -1) >= PS_ONE;
-    };
-    // look back for the segment start
-    uint32_t s0 = t0;
-    {
-        uint32_t back = 0;
-        unsigned long long fi;
-        int g;
-        while (s0 > 0 && !classify(s0 - 1, fi, g)) {
-            --s0;
-            if (++back > PS_MAX_LOOKBACK) {          // a carrier slower than 0.7 Hz: leave it to the serial chain
-                atomicOr(S.status + 3, 1u);
-                return;
-            }
-        }
+    const bool live = t0_ < S.n;                                 // dead lanes stay with the warp: no divergent exits
+    const uint32_t t0 = live ? (uint32_t)t0_ : 0u;
+    const uint32_t t1 = live ? (uint32_t)min((uint64_t)S.n, t0_ + PS_BLOCK) : 0u;
+    // Look back for the segment start, 4 class bytes at a time (t0 is a multiple of 256, so s0 stays 4-aligned).
+    uint32_t s0 = t0, back = 0;
+    uint32_t w4 = 0;
+    while (s0 >= 4 && back <= PS_MAX_LOOKBACK) {
+        w4 = __ldg(reinterpret_cast<const uint32_t*>(S.cls + s0 - 4)) & 0x20202020u;
+        if (w4) break;
+        s0 -= 4;
+        back += 4;
     }
+    __syncwarp();
+    if (back > PS_MAX_LOOKBACK) atomicOr(S.status + 3, 1u);      // a carrier slower than 0.7 Hz: serial chain instead
+    if (w4) s0 = s0 - 4 + ((31 - __clz(w4)) >> 3) + 1;           // first step after the last wrap
     unsigned long long L = (s0 == 0) ? (S.p0 & 0x1FFFFull) : 0ull;
-    for (uint32_t s = s0; s < t1; ++s) {
-        unsigned long long fi;
-        int g;
-        const bool wraps = classify(s, fi, g);
-        // The low bits decide the rounding.  Only an exact tie on a wrap step (g == 17, low 17 bits == 2^16)
-        // needs a bit from above them: the parity of the high part.  Those steps are rounded DOWN here and
-        // flagged; k_ps_parity_* resolves them with an exact parity scan (common when the pitch is 0.25).
+    // one step: the low bits decide the rounding.  Only an exact tie on a wrap step (g == 17, low 17 bits == 2^16)
+    // needs a bit from above them: the parity of the high part.  Those steps are rounded DOWN here and flagged;
+    // k_ps_parity_* resolves them with an exact parity scan (common when the pitch is 0.25).
+    auto step = [&](float f, unsigned c, unsigned long long& inc, unsigned& flag) {
+        const unsigned long long fi = ps_fix(f);
+        const int g = (int)(c & 31u);
         const unsigned long long xl = L + fi;
         const bool tie = (g == 17) && ((xl & 0x1FFFFull) == 0x10000ull);
         const unsigned long long r = tie ? (xl & ~0x1FFFFull) : ps_rhe(xl, g, -1);
-        if (s >= t0) {
-            S.inc[s] = r - L;
-            S.sflag[s] = tie ? (unsigned char)(2u | (((xl >> 17) & 1ull) << 2)) : (unsigned char)((r >> 17) & 1ull);
-        }
-        L = wraps ? 0ull : (r & 0x1FFFFull);         // after a wrap the phase is a multiple of 2^-23: no low bits
+        inc = r - L;
+        flag = tie ? (2u | (unsigned)(((xl >> 17) & 1ull) << 2)) : (unsigned)((r >> 17) & 1ull);
+        L = (c & 32u) ? 0ull : (r & 0x1FFFFull);   // after a wrap the phase is a multiple of 2^-23: no low bits
+    };
+    unsigned long long inc;
+    unsigned flag;
+    for (uint32_t s = s0; s < t0; ++s) step(__ldg(S.F + s), __ldg(S.cls + s), inc, flag);
+    __syncwarp();
+    // Parity of the high part Q = floor(P / 2^17): a non-tie step adds a known carry (bit 0 of its flag); a tie step
+    // rounds to even, so Q is even after it whatever came before.  Per block the parity map is either p -> p ^ x or
+    // the constant x, which composes associatively (k_ps_parity_spine scans it over the blocks).
+    unsigned px = 0, has_tie = 0;
+    auto parity = [&](unsigned fl) { if (fl & 2u) { has_tie = 1; px = 0; } else px ^= fl & 1u; };
+    // own block, four steps at a time: 16 bytes of F and 4 class bytes in, one full 32-byte sector of increments
+    // and 4 flag bytes out
+    uint32_t s = t0;
+    for (; s + 4 <= t1; s += 4) {
+        const float4 f4 = __ldg(reinterpret_cast<const float4*>(S.F + s));
+        const uint32_t c4 = __ldg(reinterpret_cast<const uint32_t*>(S.cls + s));
+        unsigned long long i0, i1, i2, i3;
+        unsigned g0, g1, g2, g3;
+        step(f4.x, c4 & 0xFFu, i0, g0);
+        step(f4.y, (c4 >> 8) & 0xFFu, i1, g1);
+        step(f4.z, (c4 >> 16) & 0xFFu, i2, g2);
+        step(f4.w, c4 >> 24, i3, g3);
+        ulonglong2* dst = reinterpret_cast<ulonglong2*>(S.inc + s);
+        dst[0] = make_ulonglong2(i0, i1);
+        dst[1] = make_ulonglong2(i2, i3);
+        *reinterpret_cast<uint32_t*>(S.sflag + s) = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+        parity(g0); parity(g1); parity(g2); parity(g3);
     }
+    for (; s < t1; ++s) {
+        step(__ldg(S.F + s), __ldg(S.cls + s), inc, flag);
+        S.inc[s] = inc;
+        S.sflag[s] = (unsigned char)flag;
+        parity(flag);
+    }
+    if (live) S.bpar[b] = (unsigned char)((has_tie << 1) | px);
+    if (__any_sync(0xffffffffu, has_tie != 0) && (threadIdx.x & 31) == 0) atomicOr(S.status + 15, 1u);   // ties exist this round
 }
 
-// Parity of the high part Q = floor(P / 2^17) along the whole utterance.  A non-tie step adds a known carry
-// (parity bit0 of its flag); a tie step rounds to even, so Q is even after it whatever came before: per block the
-// parity map is either p -> p ^ x or the constant x, which composes associatively (a scan over blocks).
-__global__ void __launch_bounds__(128) k_ps_parity_block(PScanDev S)
-{
-    if (S.status[1] | S.status[3]) return;
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t t0 = (uint64_t)b * PS_BLOCK;
-    if (t0 >= S.n) return;
-    const uint32_t t1 = (uint32_t)min((uint64_t)S.n, t0 + PS_BLOCK);
-    unsigned x = 0, has_tie = 0;
-    for (uint32_t t = (uint32_t)t0; t < t1; ++t) {
-        const unsigned f = S.sflag[t];
-        if (f & 2u) { has_tie = 1; x = 0; } else x ^= f & 1u;
-    }
-    S.bpar[b] = (unsigned char)((has_tie << 1) | x);
-}
 // exclusive scan of the block transducers -> incoming parity of every block (one CTA walks the spine)
 __global__ void __launch_bounds__(1024) k_ps_parity_spine(PScanDev S, uint32_t nblk)
 {
-    if (S.status[1] | S.status[3]) return;
+    if (S.status[1] | S.status[3] | (S.status[15] ^ 1u)) return;     // no tie anywhere this round: nothing to fix
     __shared__ unsigned sh[32];
     __shared__ unsigned carry;                       // parity entering the current stripe
     if (threadIdx.x == 0) carry = (unsigned)((S.p0 >> 17) & 1ull);
@@ -796,7 +835,7 @@ __global__ void __launch_bounds__(1024) k_ps_parity_spine(PScanDev S, uint32_t n
 // second walk with the incoming parity known: round every flagged tie to even
 __global__ void __launch_bounds__(128) k_ps_parity_fix(PScanDev S)
 {
-    if (S.status[1] | S.status[3]) return;
+    if (S.status[1] | S.status[3] | (S.status[15] ^ 1u)) return;
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t t0 = (uint64_t)b * PS_BLOCK;
     if (t0 >= S.n) return;
@@ -813,31 +852,15 @@ __global__ void __launch_bounds__(128) k_ps_parity_fix(PScanDev S)
     }
 }
 
-// fully parallel proof: every step, redone with real f32 operations, must land on the next phase
-__global__ void k_ps_verify(PScanDev S)
-{
-    if (S.status[1] | S.status[3]) return;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    bool bad = false;
-    if (t < S.n) {
-        const unsigned long long p = S.P[t], q = S.P[t + 1];
-        const float a = __ull2float_rn(p) * 9.094947017729282e-13f;       // * 2^-40
-        const float c = __ull2float_rn(q) * 9.094947017729282e-13f;
-        bad = ((unsigned long long)(a * 1099511627776.0f) != p) || ((unsigned long long)(c * 1099511627776.0f) != q);
-        float nx = sadd(a, S.F[t]);                                       // :520
-        if (nx >= 1.0f) nx = ssub(nx, 1.0f);                              // :523-525
-        bad |= __float_as_uint(nx) != __float_as_uint(c);
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, bad);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(S.status, (unsigned)__popc(m));
-}
+// end of a round: status[0] holds the steps whose f32 redo missed the next phase (counted by k_ps_scan_apply)
 __global__ void k_ps_check(PScanDev S)
 {
     if (S.status[1] | S.status[3]) return;
-    if (S.status[2] < 12u) S.status[4 + S.status[2]] = S.status[0];   // mismatch history (diagnostics)
+    if (S.status[2] < 11u) S.status[4 + S.status[2]] = S.status[0];   // mismatch history (diagnostics)
     S.status[2] += 1;
     if (S.status[0] == 0) S.status[1] = 1;      // converged: exact
     S.status[0] = 0;
+    S.status[15] = 0;
 }
 
 // phases -> polyBLEP saw in the tiled layout k_formant reads (same arithmetic as k_phase_pair's saw warp)

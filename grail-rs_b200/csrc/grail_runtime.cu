@@ -574,14 +574,15 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
         void *p = nullptr, *q = nullptr, *b = nullptr;
         int rc1 = pool_alloc(ctx, (n + 1) * 8, &p);
         if (!rc1) { pl->pscan_bufs.push_back(p); rc1 = pool_alloc(ctx, n * 8 + 8, &q); }
-        void *fl = nullptr, *bp = nullptr;
+        void *fl = nullptr, *bp = nullptr, *cl = nullptr;
         if (!rc1) { pl->pscan_bufs.push_back(q); rc1 = pool_alloc(ctx, nb * 8 + 8, &b); }
         if (!rc1) { pl->pscan_bufs.push_back(b); rc1 = pool_alloc(ctx, n + 16, &fl); }
         if (!rc1) { pl->pscan_bufs.push_back(fl); rc1 = pool_alloc(ctx, n / PS_BLOCK + 16, &bp); }
+        if (!rc1) { pl->pscan_bufs.push_back(bp); rc1 = pool_alloc(ctx, n + 16, &cl); }
         if (rc1) return fail(rc1);
-        pl->pscan_bufs.push_back(bp);
+        pl->pscan_bufs.push_back(cl);
         S.P = (unsigned long long*)p; S.inc = (unsigned long long*)q; S.bsum = (unsigned long long*)b;
-        S.sflag = (unsigned char*)fl; S.bpar = (unsigned char*)bp;
+        S.sflag = (unsigned char*)fl; S.bpar = (unsigned char*)bp; S.cls = (unsigned char*)cl;
         S.n = U.n_samples;
         S.p0 = (unsigned long long)(U.init_phase * 1099511627776.0f);
         pl->pscans.push_back(S);
@@ -690,24 +691,22 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
         CU(ctx, cudaMemsetAsync(S.status, 0, 64, s));
         const uint32_t n = S.n, nb = (uint32_t)(((uint64_t)n + 1 + SCAN_TILE - 1) / SCAN_TILE);
         const uint32_t g256 = (n + 255) / 256;
-        auto scan = [&]() {
+        auto scan = [&](int verify) {
             k_ps_scan_reduce<<<nb, SCAN_THREADS, 0, s>>>(S);
             k_ps_scan_spine<<<1, 1024, 0, s>>>(S, nb);
-            k_ps_scan_apply<<<nb, SCAN_THREADS, 0, s>>>(S);
+            k_ps_scan_apply<<<nb, SCAN_THREADS, 0, s>>>(S, verify);
         };
         k_ps_init<<<g256, 256, 0, s>>>(S);
-        scan();                                            // round 0: unrounded prefix sum
+        scan(0);                                           // round 0: unrounded prefix sum
         pl->last_launches += 4;
         for (int r = 0; r < PS_MAX_ROUNDS; ++r) {          // every kernel returns at once after convergence
             const uint32_t nblk = (n + PS_BLOCK - 1) / PS_BLOCK;
             k_ps_replay<<<(nblk + 127) / 128, 128, 0, s>>>(S);
-            k_ps_parity_block<<<(nblk + 127) / 128, 128, 0, s>>>(S);
             k_ps_parity_spine<<<1, 1024, 0, s>>>(S, nblk);
             k_ps_parity_fix<<<(nblk + 127) / 128, 128, 0, s>>>(S);
-            scan();
-            k_ps_verify<<<g256, 256, 0, s>>>(S);
+            scan(1);
             k_ps_check<<<1, 1, 0, s>>>(S);
-            pl->last_launches += 9;
+            pl->last_launches += 7;
         }
         k_ps_saw<<<((n + 7) / 8 + 255) / 256, 256, 0, s>>>(S, P, u);
         pl->last_launches++;
@@ -1038,7 +1037,7 @@ int grail_cuda_plan_phase_scan_stats(grail_plan* plan, uint32_t* stats)
         stats[3] += st[16 * i + 3] ? 1u : 0u;
         if (getenv("GRAIL_PSCAN_DEBUG")) {
             fprintf(stderr, "pscan %zu: done %u rounds %u refused %u mismatches per round:", i, st[16 * i + 1], st[16 * i + 2], st[16 * i + 3]);
-            for (int r = 0; r < 12; ++r) fprintf(stderr, " %u", st[16 * i + 4 + r]);
+            for (int r = 0; r < 11; ++r) fprintf(stderr, " %u", st[16 * i + 4 + r]);
             fprintf(stderr, "\n");
         }
     }
