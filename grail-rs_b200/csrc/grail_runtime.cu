@@ -43,7 +43,8 @@ struct grail_ctx {
     uint32_t min_chunk = 2048;
     uint32_t max_chunk = 1u << 22;
     int      debug_taps = 0;
-    uint32_t pscan_min = 1u << 20;   // utterances at least this long get the exact parallel phase scan
+    uint32_t pscan_min = 1u << 18;   // utterances at least this long may get the exact parallel phase scan
+    int pscan_cost_model = 1;        // 0: scan every utterance >= pscan_min (at most 16), whatever it costs
     int      zero_copy_out = 0;      // 1: k_formant stores straight into pinned host output (measured slower: 23 vs 50 GB/s over PCIe)
     int      formants_per_lane = 2;  // 1 or 2 formants of an utterance share one lane's clocks, noise and saw
     // pinned staging for pageable D2H
@@ -522,17 +523,31 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
     pl->n_groups = (pl->n_items + 31) / 32;
     pl->saw_words = (uint64_t)pl->n_groups * 32ull * pl->chunk_len;
 
-    // ---- long utterances: exact parallel phase scan instead of the serial chain (a handful at most; with many
-    //      long utterances the chains of k_phase_pair already run concurrently)
+    // ---- long utterances: exact parallel phase scan instead of the serial chain.  The chains of k_phase_pair run
+    //      concurrently, so that kernel lasts as long as its longest utterance (4.7 ns/sample measured); a scan costs
+    //      about 0.45 ms of launches plus 0.16 ns/sample and scans run one after another.  Take the k longest
+    //      utterances (k <= 16) that minimise scans + longest remaining chain.
     {
         std::vector<uint32_t> longs;
         for (uint32_t u = 0; u < n_utts; ++u)
             if (pl->utts[u].n_samples >= ctx->pscan_min) longs.push_back(u);
-        if (!longs.empty() && longs.size() <= 16) {
-            for (uint32_t u : longs) {
-                pl->utts[u].pscan = (int32_t)pl->pscan_utt.size();
-                pl->pscan_utt.push_back(u);
-            }
+        std::sort(longs.begin(), longs.end(), [&](uint32_t a, uint32_t b) { return pl->utts[a].n_samples > pl->utts[b].n_samples; });
+        uint32_t rest_max = 0;                           // longest utterance below the threshold
+        for (uint32_t u = 0; u < n_utts; ++u)
+            if (pl->utts[u].n_samples < ctx->pscan_min) rest_max = std::max(rest_max, pl->utts[u].n_samples);
+        auto chain_ms = [](uint32_t n) { return 4.7e-6 * (double)n; };
+        auto scan_ms = [](uint32_t n) { return 0.45 + 0.16e-6 * (double)n; };
+        size_t best_k = 0;
+        double best = chain_ms(longs.empty() ? rest_max : std::max(rest_max, pl->utts[longs[0]].n_samples)), scans = 0.0;
+        for (size_t k = 1; k <= longs.size() && k <= 16; ++k) {
+            scans += scan_ms(pl->utts[longs[k - 1]].n_samples);
+            const uint32_t next = k < longs.size() ? pl->utts[longs[k]].n_samples : 0u;
+            const double t = scans + chain_ms(std::max(rest_max, next));
+            if (t < best || !ctx->pscan_cost_model) { best = t; best_k = k; }
+        }
+        for (size_t i = 0; i < best_k; ++i) {
+            pl->utts[longs[i]].pscan = (int32_t)pl->pscan_utt.size();
+            pl->pscan_utt.push_back(longs[i]);
         }
     }
 
@@ -699,7 +714,10 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
         k_ps_init<<<g256, 256, 0, s>>>(S);
         scan(0);                                           // round 0: unrounded prefix sum
         pl->last_launches += 4;
-        for (int r = 0; r < PS_MAX_ROUNDS; ++r) {          // every kernel returns at once after convergence
+        // measured: 1-2 rounds at 44 k samples, 3 at 0.4-1.3 M, 5 at 26 M; enqueue about twice that
+        int rounds = 4;
+        for (uint64_t m = 1ull << 18; m < n && rounds < PS_MAX_ROUNDS; m <<= 1) ++rounds;
+        for (int r = 0; r < rounds; ++r) {                 // every kernel returns at once after convergence
             const uint32_t nblk = (n + PS_BLOCK - 1) / PS_BLOCK;
             k_ps_replay<<<(nblk + 127) / 128, 128, 0, s>>>(S);
             k_ps_parity_spine<<<1, 1024, 0, s>>>(S, nblk);
@@ -863,6 +881,8 @@ int grail_cuda_set_option(grail_ctx* ctx, const char* key, double value)
         ctx->formants_per_lane = (int)value;
     } else if (!strcmp(key, "pipeline")) {
         ctx->pipeline = value != 0.0;
+    } else if (!strcmp(key, "pscan_cost_model")) {
+        ctx->pscan_cost_model = value != 0.0;
     } else if (!strcmp(key, "pscan_min_samples")) {
         ctx->pscan_min = value < 1.0 ? 1u : (value > 4.0e9 ? 0xFFFFFFFFu : (uint32_t)value);
     } else if (!strcmp(key, "zero_copy_out")) {

@@ -107,7 +107,7 @@ int  grail_cuda_synchronize(grail_ctx* ctx);
 /* tuning knobs: "warmup_nepers" (float, filter warm-up depth, default 13.8 ~ 1e-6),
  * "target_lanes" (int, time-chunks the planner aims for), "max_chunk" / "min_chunk" (samples),
  * "formants_per_lane" (1|2), "pipeline" (0|1: overlap consecutive launches of a plan), "pscan_min_samples",
- * "zero_copy_out" (0|1) */
+ * "pscan_cost_model" (0|1), "zero_copy_out" (0|1) */
 int  grail_cuda_set_option(grail_ctx* ctx, const char* key, double value);
 
 /* pinned host memory for full-rate H2D/D2H (optional; pageable buffers also work) */
@@ -156,8 +156,9 @@ int  grail_cuda_plan_device_output(grail_plan* plan, int format, void** out_dptr
 /* D2H of the packed output into a host buffer (chunked, through pinned staging if pageable) */
 int  grail_cuda_plan_read_output(grail_plan* plan, int format, void* host_out);
 int  grail_cuda_plan_timings(const grail_plan* plan, grail_timings* out);
-/* Long utterances (>= option "pscan_min_samples", default 2^20) get their carrier phase from the exact parallel
- * phase scan instead of the serial chain.  stats[4] = {scans in this plan, scans that converged (the rest fell back
+/* Long utterances (>= option "pscan_min_samples", "pscan_cost_model" (0|1), default 2^18) may get their carrier phase from the exact parallel
+ * phase scan instead of the serial chain: the k <= 16 longest that minimise (scans + longest remaining chain) under
+ * a measured cost model; option "pscan_cost_model" = 0 scans every utterance over the threshold (tests).  stats[4] = {scans in this plan, scans that converged (the rest fell back
  * to the serial chain), largest number of refinement rounds used, scans refused (an F_t outside [2^-16, 0.5])}
  * for the most recent launch. */
 int  grail_cuda_plan_phase_scan_stats(grail_plan* plan, uint32_t* stats);

@@ -7,6 +7,7 @@ from grail_rs_b200 import workloads as W
 from oracle import oracle as O
 ctx = g.Context(0)
 ctx.set_option("pscan_min_samples", 1)
+ctx.set_option("pscan_cost_model", 0)
 v = g.voices.generic()
 for name, (elems, offs, vp) in [("voiced2", W.from_phonemes([[3, 4]], v, [3])), ("sil", W.from_phonemes([[0, 0]], v, [1])), ("mixed", W.from_phonemes([[0, 4, 3, 0, 0, 3]], v, [1]))]:
     plan = ctx.plan(elems, offs, vp)

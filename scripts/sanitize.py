@@ -11,6 +11,7 @@ elems = elems.copy(); elems["length"] = 0.05
 out, oo = ctx.synthesize_batch(elems, offs, vp)
 print("batch", len(out), float(np.abs(out).sum()))
 ctx.set_option("pscan_min_samples", 1)
+ctx.set_option("pscan_cost_model", 0)
 out2, _ = ctx.synthesize_batch(elems, offs, vp)
 print("pscan", float(np.abs(out2 - out).max()))
 e4, o4, v4 = W.config4(3, first_utt=7)

@@ -79,6 +79,7 @@ def test_parallel_phase_scan_matches_chain(ctx, oracle):
     """the exact parallel phase scan (forced on short inputs) against the oracle's f32 chain, bit for bit: voiced,
     silence-heavy (frequency 0.25: a wrap every 4 samples, exact ties on wrap steps) and random-pitch inputs"""
     ctx.set_option("pscan_min_samples", 1)
+    ctx.set_option("pscan_cost_model", 0)
     try:
         v = g.voices.generic()
         cases = [W.from_phonemes([[0, 4, 3, 3, 4, 3]], v, [3]), W.from_phonemes([[0, 0, 0, 3, 0, 0, 4, 0]], v, [1]),
@@ -99,4 +100,5 @@ def test_parallel_phase_scan_matches_chain(ctx, oracle):
             print(ps)
             plan.close()
     finally:
-        ctx.set_option("pscan_min_samples", 1 << 20)
+        ctx.set_option("pscan_min_samples", 1 << 18)
+        ctx.set_option("pscan_cost_model", 1)
