@@ -17,6 +17,7 @@ ELEM_DT = np.dtype([
     ("formant_breath", "<f4", (NF,)), ("formant_turb", "<f4", (NF,)), ("formant_amp", "<f4", (NF,)),
 ])
 SEQ_ELEM_DT = np.dtype([("has_elem", "<u4"), ("elem", ELEM_DT), ("length", "<f4"), ("blend_length", "<f4")])
+PHONEME_ELEM_DT = np.dtype([("phoneme", "<u4"), ("length", "<f4"), ("blend_length", "<f4"), ("frequency", "<f4")])   # 16 B
 VOICE_DT = np.dtype([
     ("sample_rate", "<f4"), ("jitter_frequency", "<f4"), ("jitter_delta_frequency", "<f4"),
     ("jitter_delta_formant_frequency", "<f4"), ("jitter_delta_amplitude", "<f4"),
@@ -46,7 +47,8 @@ EXPORTS = [
     "grail_cuda_abi_version", "grail_cuda_device_count", "grail_cuda_status_string", "grail_cuda_create",
     "grail_cuda_destroy", "grail_cuda_last_error", "grail_cuda_stream_handle", "grail_cuda_synchronize",
     "grail_cuda_set_option", "grail_cuda_host_alloc", "grail_cuda_host_free", "grail_cuda_count_samples",
-    "grail_cuda_synthesize_batch", "grail_cuda_plan_create", "grail_cuda_plan_destroy",
+    "grail_cuda_synthesize_batch", "grail_cuda_plan_create", "grail_cuda_plan_create_phoneme_elems",
+    "grail_cuda_plan_create_phonemes", "grail_cuda_plan_destroy",
     "grail_cuda_plan_join", "grail_cuda_plan_total_samples", "grail_cuda_plan_out_offsets", "grail_cuda_plan_launch", "grail_cuda_plan_launch_interleaved",
     "grail_cuda_plan_device_output", "grail_cuda_plan_read_output", "grail_cuda_plan_timings",
     "grail_cuda_plan_read_intermediates", "grail_cuda_plan_phase_scan_stats", "grail_cuda_stream_new", "grail_cuda_stream_push",
@@ -80,6 +82,8 @@ def lib() -> C.CDLL:
         "grail_cuda_count_samples": (i32, [vp, vp, vp, u32, vp]),
         "grail_cuda_synthesize_batch": (i32, [vp, vp, vp, vp, u32, vp, vp, i32]),
         "grail_cuda_plan_create": (i32, [vp, vp, vp, vp, u32, C.POINTER(vp)]),
+        "grail_cuda_plan_create_phoneme_elems": (i32, [vp, vp, vp, vp, u32, u32, vp, vp, u32, C.POINTER(vp)]),
+        "grail_cuda_plan_create_phonemes": (i32, [vp, vp, vp, vp, vp, u32, u32, vp, vp, u32, C.POINTER(vp)]),
         "grail_cuda_plan_destroy": (None, [vp]),
         "grail_cuda_plan_join": (i32, [vp]),
         "grail_cuda_plan_total_samples": (u64, [vp]),

@@ -43,6 +43,17 @@ struct UttDev {
     uint64_t sample0;              // absolute index of sample 0 in its stream (aspiration-noise draw index)
 };
 
+// phoneme-level input of a plan: Selector and the Intonator stub run on the device
+struct SelectDev {
+    const grail_phoneme_elem* ph;  // PhonemeElem records, or
+    const uint8_t* ids;            // bare phoneme ids with
+    const float* center;           // one centre frequency per utterance
+    const float* storages;         // [n_storages][n_sounds][49]
+    const uint32_t* utt_storage;   // per utterance, null = 0
+    uint32_t n_sounds, n_elems, n_utts;
+};
+constexpr uint32_t SELECT_WORDS = sizeof(grail_seq_elem) / 4;   // 52
+
 struct JitSchedDev {
     float    inc;                  // voice.jitter_frequency
     float    phase0;               // value-noise phase before sample 0
@@ -105,6 +116,43 @@ __device__ __forceinline__ uint32_t last_le(uint32_t n, F key, int64_t v)
     }
     return lo;
 }
+
+// Selector::next (src/lib.rs:987-1005): phoneme -> Option<SynthesisElem> from the voice storage, with
+// copy_with_frequency (:445-450: frequency.min(0.5)); with bare ids also Intonator::next (:1057-1075: length 0.5,
+// blend 0.5, the voice's centre frequency).  One thread per 32-bit word of the 208-byte Sequencer record.
+__global__ void k_select(uint32_t* __restrict__ elems, const UttDev* __restrict__ utts, SelectDev S)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t p = (uint32_t)(t / SELECT_WORDS), w = (uint32_t)(t % SELECT_WORDS);
+    if (p >= S.n_elems) return;
+    uint32_t lo = 0, hi = S.n_utts;                          // last utterance whose first element is <= p
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (utts[mid].elem_first <= p) lo = mid; else hi = mid;
+    }
+    uint32_t id;
+    float len, bl, fr;
+    if (S.ph) {
+        const grail_phoneme_elem e = S.ph[p];
+        id = e.phoneme; len = e.length; bl = e.blend_length; fr = e.frequency;
+    } else {
+        id = S.ids[p]; len = 0.5f; bl = 0.5f; fr = S.center[lo];
+    }
+    const bool sound = id >= GRAIL_PHONEME_FIRST_SOUND;
+    uint32_t v = 0;
+    if (w == 0) v = sound ? 1u : 0u;
+    else if (w == SELECT_WORDS - 2) v = __float_as_uint(len);
+    else if (w == SELECT_WORDS - 1) v = __float_as_uint(bl);
+    else if (sound) {
+        if (w == 1) v = __float_as_uint(fminf(fr, 0.5f));
+        else {
+            const uint32_t st = S.utt_storage ? S.utt_storage[lo] : 0u;
+            v = __float_as_uint(S.storages[((size_t)st * S.n_sounds + (id - GRAIL_PHONEME_FIRST_SOUND)) * 49u + (w - 1)]);
+        }
+    }
+    elems[t] = v;
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // K0: jitter schedule.  One lane per distinct jitter_frequency; walks the value-noise phase clock

@@ -152,6 +152,7 @@ struct grail_plan {
     std::vector<PScanDev> pscans;          // exact parallel phase scans (one per long utterance)
     std::vector<uint32_t> pscan_utt;
     uint32_t* d_pscan_status = nullptr;
+    bool select_on_device = false;   // d_elems was written by k_select from phoneme-level input
     std::vector<void*> pscan_bufs;
     bool jit_on_host = false;   // few distinct jitter increments: schedules computed by the planner
     std::vector<JitRec> jrecs;
@@ -193,15 +194,44 @@ struct StreamStart {
 };
 
 
-static int64_t schedule_utterance(const grail_seq_elem* e, uint32_t n_elems, float sample_rate, SegRec* segs,
-                                  SeqCache& cache, const StreamStart* ss = nullptr, float* t_neg_out = nullptr)
+// What a plan is built from: Sequencer input records (the path's own boundary), or phoneme-level input that the
+// device expands with k_select (Selector, src/lib.rs:987-1005; Intonator stub, :1057-1075).  The host only ever
+// needs each element's length, whether it has a sound, and which formant amplitudes are non-zero.
+struct ElemInput {
+    const grail_seq_elem* full = nullptr;
+    const grail_phoneme_elem* ph = nullptr;     // PhonemeElem records, or
+    const uint8_t* ids = nullptr;               // bare phoneme ids (Intonator on the device too)
+    const float* center = nullptr;              // per utterance, with ids
+    const grail_elem* storages = nullptr;       // n_storages x n_sounds
+    uint32_t n_sounds = 0, n_storages = 0;
+    const uint32_t* utt_storage = nullptr;      // per utterance, null = storage 0
+
+    bool phoneme_level() const { return full == nullptr && (ph != nullptr || ids != nullptr); }
+    float length(uint32_t p) const { return full ? full[p].length : (ph ? ph[p].length : 0.5f); }   // :1069
+    uint32_t phoneme(uint32_t p) const { return ph ? ph[p].phoneme : (uint32_t)ids[p]; }
+    bool has_elem(uint32_t p) const
+    {
+        if (full) return full[p].has_elem != 0;
+        return phoneme(p) >= GRAIL_PHONEME_FIRST_SOUND;                                             // :658
+    }
+    float amp(uint32_t u, uint32_t p, int i) const
+    {
+        if (full) return full[p].elem.formant_amp[i];
+        const uint32_t st = utt_storage ? utt_storage[u] : 0u;
+        return storages[(size_t)st * n_sounds + (phoneme(p) - GRAIL_PHONEME_FIRST_SOUND)].formant_amp[i];
+    }
+};
+
+template <class LenFn>
+static int64_t schedule_utterance_fn(LenFn length_of, uint32_t n_elems, float sample_rate, SegRec* segs,
+                                     SeqCache& cache, const StreamStart* ss = nullptr, float* t_neg_out = nullptr)
 {
     const float dt = sdiv(1.0f, sample_rate);       // src/lib.rs:944
     float t_neg = ssub(0.0f, dt);                   // first call: time = 0 - delta_time  (:861)
     if (ss && !ss->fresh) t_neg = ss->t_neg;
     uint64_t n = 0;
     for (uint32_t p = 0; p < n_elems; ++p) {
-        const float len = e[p].length;
+        const float len = length_of(p);
         float time0 = sadd(t_neg, len);             // :873 / :882
         if (p == 0 && ss && ss->cont_phoneme) time0 = ss->time0;   // a phoneme already in progress
         if (segs) { segs[p].start = (uint32_t)n; segs[p].time0 = time0; }
@@ -225,11 +255,29 @@ static int64_t schedule_utterance(const grail_seq_elem* e, uint32_t n_elems, flo
     return (int64_t)n;
 }
 
-static int validate_inputs(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_t* utt_offsets,
+static int64_t schedule_utterance(const grail_seq_elem* e, uint32_t n_elems, float sample_rate, SegRec* segs,
+                                  SeqCache& cache, const StreamStart* ss = nullptr, float* t_neg_out = nullptr)
+{
+    return schedule_utterance_fn([e](uint32_t p) { return e[p].length; }, n_elems, sample_rate, segs, cache, ss, t_neg_out);
+}
+
+static int validate_inputs(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_offsets,
                            const grail_voice_params* voices, uint32_t n_utts)
 {
-    if (!utt_offsets || !voices || (n_utts && !elems && utt_offsets[n_utts] != 0))
+    if (!utt_offsets || !voices || (n_utts && !in.full && !in.phoneme_level() && utt_offsets[n_utts] != 0))
         return set_err(ctx, GRAIL_ERR_INVALID_ARG, "null input pointer");
+    if (in.phoneme_level()) {
+        if (!in.storages || in.n_sounds == 0 || in.n_storages == 0 || (in.ids && !in.center))
+            return set_err(ctx, GRAIL_ERR_INVALID_ARG, "phoneme-level input needs a voice storage (and centre frequencies with bare ids)");
+        for (uint32_t u = 0; u < n_utts; ++u) {
+            if (in.utt_storage && in.utt_storage[u] >= in.n_storages)
+                return set_err(ctx, GRAIL_ERR_INVALID_ARG, "utterance %u: voice storage index %u out of range", u, in.utt_storage[u]);
+            if (utt_offsets[u + 1] < utt_offsets[u]) continue;          // reported below
+            for (uint32_t p = utt_offsets[u]; p < utt_offsets[u + 1]; ++p)
+                if (in.phoneme(p) >= GRAIL_PHONEME_FIRST_SOUND + in.n_sounds)
+                    return set_err(ctx, GRAIL_ERR_INVALID_ARG, "utterance %u: phoneme id %u has no entry in the voice storage", u, in.phoneme(p));
+        }
+    }
     for (uint32_t u = 0; u < n_utts; ++u) {
         if (utt_offsets[u + 1] < utt_offsets[u])
             return set_err(ctx, GRAIL_ERR_INVALID_ARG, "utt_offsets not monotone at %u", u);
@@ -247,7 +295,7 @@ static int validate_inputs(grail_ctx* ctx, const grail_seq_elem* elems, const ui
             !std::isfinite(v.jitter_delta_amplitude))
             return set_err(ctx, GRAIL_ERR_INVALID_ARG, "utterance %u: non-finite jitter scalar", u);
         for (uint32_t p = utt_offsets[u]; p < utt_offsets[u + 1]; ++p)
-            if (!std::isfinite(elems[p].length))
+            if (!std::isfinite(in.length(p)))
                 return set_err(ctx, GRAIL_ERR_INVALID_ARG, "utterance %u: non-finite phoneme length", u);
     }
     return GRAIL_OK;
@@ -349,12 +397,12 @@ static void plan_release(grail_plan* pl)
     delete pl;
 }
 
-static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_t* utt_offsets,
+static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_offsets,
                       const grail_voice_params* voices, uint32_t n_utts, grail_plan** out_plan,
                       const StreamStart* ss = nullptr, bool pipelined = false)
 {
     if (ss && n_utts != 1) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "a stream window is one utterance");
-    int rc = validate_inputs(ctx, elems, utt_offsets, voices, n_utts);
+    int rc = validate_inputs(ctx, in, utt_offsets, voices, n_utts);
     if (rc) return rc;
     CU(ctx, cudaSetDevice(ctx->device));
     grail_plan* pl = new (std::nothrow) grail_plan();
@@ -378,8 +426,9 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
         memset(&U, 0, sizeof U);
         U.elem_first = utt_offsets[u];
         U.n_elems = utt_offsets[u + 1] - utt_offsets[u];
-        const grail_seq_elem* e = elems + U.elem_first;
-        int64_t n = schedule_utterance(e, U.n_elems, voices[u].sample_rate, pl->segs.data() + U.elem_first, cache, ss);
+        const uint32_t e0 = U.elem_first;
+        int64_t n = schedule_utterance_fn([&in, e0](uint32_t p) { return in.length(e0 + p); }, U.n_elems, voices[u].sample_rate,
+                                          pl->segs.data() + U.elem_first, cache, ss);
         if (n >= 0 && ss) {
             // an unfinished stream holds its last element back as look-ahead: only the phonemes before it are due
             if (!ss->finished && U.n_elems > 0) n = (int64_t)pl->segs[U.elem_first + U.n_elems - 1].start;
@@ -408,7 +457,7 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
         for (int i = 0; i < NF; ++i) {
             bool act = false;
             for (uint32_t p = 0; p < U.n_elems && !act; ++p)
-                act = e[p].has_elem && !(e[p].elem.formant_amp[i] == 0.0f);
+                act = in.has_elem(e0 + p) && !(in.amp(u, e0 + p, i) == 0.0f);
             // a continued stream: a formant that is still ringing stays active whatever the new elements say
             if (ss && ss->filter_state)
                 act = act || ss->filter_state[i] != 0.0f || ss->filter_state[8 + i] != 0.0f || ss->filter_state[16 + i] != 0.0f;
@@ -603,9 +652,40 @@ static int plan_build(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_
         pl->pscans.push_back(S);
     }
     cudaStream_t s = ctx->stream;
-    if (pl->n_elems) CUF(cudaMemcpyAsync(pl->d_elems, elems, (size_t)pl->n_elems * sizeof(grail_seq_elem), cudaMemcpyHostToDevice, s));
+    if (pl->n_elems && in.full)
+        CUF(cudaMemcpyAsync(pl->d_elems, in.full, (size_t)pl->n_elems * sizeof(grail_seq_elem), cudaMemcpyHostToDevice, s));
     CUF(cudaMemcpyAsync(pl->d_segs, pl->segs.data(), pl->segs.size() * sizeof(SegRec), cudaMemcpyHostToDevice, s));
     if (n_utts) CUF(cudaMemcpyAsync(pl->d_utts, pl->utts.data(), n_utts * sizeof(UttDev), cudaMemcpyHostToDevice, s));
+    if (pl->n_elems && in.phoneme_level()) {
+        // Selector (and, for bare ids, the Intonator stub) on the device: 1-16 bytes per phoneme cross PCIe instead of 208
+        SelectDev S;
+        memset(&S, 0, sizeof S);
+        auto up = [&](const void* host, size_t bytes, const void** dev) -> int {
+            void* d = nullptr;
+            int rc_ = pool_alloc(ctx, bytes + 16, &d);
+            if (rc_) return rc_;
+            pl->pscan_bufs.push_back(d);                       // freed with the plan
+            if (cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return GRAIL_ERR_CUDA;
+            *dev = d;
+            return 0;
+        };
+        int rcs = 0;
+        if (in.ph) rcs = up(in.ph, (size_t)pl->n_elems * sizeof(grail_phoneme_elem), (const void**)&S.ph);
+        else {
+            rcs = up(in.ids, (size_t)pl->n_elems, (const void**)&S.ids);
+            if (!rcs) rcs = up(in.center, (size_t)n_utts * 4, (const void**)&S.center);
+        }
+        if (!rcs) rcs = up(in.storages, (size_t)in.n_storages * in.n_sounds * sizeof(grail_elem), (const void**)&S.storages);
+        if (!rcs && in.utt_storage) rcs = up(in.utt_storage, (size_t)n_utts * 4, (const void**)&S.utt_storage);
+        if (rcs) return fail(rcs == GRAIL_ERR_CUDA ? set_err(ctx, GRAIL_ERR_CUDA, "upload of phoneme-level input failed") : rcs);
+        S.n_sounds = in.n_sounds;
+        S.n_elems = pl->n_elems;
+        S.n_utts = n_utts;
+        const uint64_t words = (uint64_t)pl->n_elems * SELECT_WORDS;
+        k_select<<<(unsigned)((words + 255) / 256), 256, 0, s>>>((uint32_t*)pl->d_elems, pl->d_utts, S);
+        CUF(cudaGetLastError());
+        pl->select_on_device = true;
+    }
     if (pl->n_items) CUF(cudaMemcpyAsync(pl->d_items, pl->items.data(), pl->n_items * sizeof(ItemDev), cudaMemcpyHostToDevice, s));
     if (pl->n_jscheds) CUF(cudaMemcpyAsync(pl->d_jscheds, pl->jscheds.data(), pl->n_jscheds * sizeof(JitSchedDev), cudaMemcpyHostToDevice, s));
     if (pl->jit_on_host && pl->n_jrecs) CUF(cudaMemcpyAsync(pl->d_jrecs, pl->jrecs.data(), (size_t)pl->n_jrecs * sizeof(JitRec), cudaMemcpyHostToDevice, s));
@@ -917,7 +997,9 @@ int grail_cuda_count_samples(const grail_seq_elem* elems, const uint32_t* utt_of
                              const grail_voice_params* voices, uint32_t n_utts, uint64_t* counts)
 {
     if (!counts) return GRAIL_ERR_INVALID_ARG;
-    int rc = validate_inputs(nullptr, elems, utt_offsets, voices, n_utts);
+    ElemInput in;
+    in.full = elems;
+    int rc = validate_inputs(nullptr, in, utt_offsets, voices, n_utts);
     if (rc) return rc;
     SeqCache cache;
     for (uint32_t u = 0; u < n_utts; ++u) {
@@ -934,13 +1016,46 @@ int grail_cuda_plan_create(grail_ctx* ctx, const grail_seq_elem* elems, const ui
 {
     if (!ctx || !out_plan) return GRAIL_ERR_INVALID_ARG;
     *out_plan = nullptr;
-    return plan_build(ctx, elems, utt_offsets, voices, n_utts, out_plan, nullptr, true);
+    ElemInput in;
+    in.full = elems;
+    return plan_build(ctx, in, utt_offsets, voices, n_utts, out_plan, nullptr, true);
 }
 
 int grail_cuda_plan_join(grail_plan* plan)
 {
     if (!plan) return GRAIL_ERR_INVALID_ARG;
     return plan_join(plan);
+}
+
+int grail_cuda_plan_create_phoneme_elems(grail_ctx* ctx, const grail_phoneme_elem* phonemes, const uint32_t* utt_offsets,
+                                         const grail_elem* storages, uint32_t n_sounds, uint32_t n_storages,
+                                         const uint32_t* utt_storage, const grail_voice_params* voices, uint32_t n_utts,
+                                         grail_plan** out_plan)
+{
+    if (!ctx || !out_plan) return GRAIL_ERR_INVALID_ARG;
+    *out_plan = nullptr;
+    if (!phonemes && n_utts && utt_offsets && utt_offsets[n_utts] != 0) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "null input pointer");
+    ElemInput in;
+    static const grail_phoneme_elem none = { 0u, 0.0f, 0.0f, 0.0f };
+    in.ph = phonemes ? phonemes : &none;
+    in.storages = storages; in.n_sounds = n_sounds; in.n_storages = n_storages; in.utt_storage = utt_storage;
+    return plan_build(ctx, in, utt_offsets, voices, n_utts, out_plan, nullptr, true);
+}
+
+int grail_cuda_plan_create_phonemes(grail_ctx* ctx, const uint8_t* phoneme_ids, const uint32_t* utt_offsets,
+                                    const float* center_frequency, const grail_elem* storages, uint32_t n_sounds,
+                                    uint32_t n_storages, const uint32_t* utt_storage, const grail_voice_params* voices,
+                                    uint32_t n_utts, grail_plan** out_plan)
+{
+    if (!ctx || !out_plan) return GRAIL_ERR_INVALID_ARG;
+    *out_plan = nullptr;
+    if (!phoneme_ids && n_utts && utt_offsets && utt_offsets[n_utts] != 0) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "null input pointer");
+    ElemInput in;
+    static const uint8_t none = 0;
+    in.ids = phoneme_ids ? phoneme_ids : &none;
+    in.center = center_frequency;
+    in.storages = storages; in.n_sounds = n_sounds; in.n_storages = n_storages; in.utt_storage = utt_storage;
+    return plan_build(ctx, in, utt_offsets, voices, n_utts, out_plan, nullptr, true);
 }
 
 void grail_cuda_plan_destroy(grail_plan* plan)
@@ -1111,7 +1226,9 @@ int grail_cuda_synthesize_batch(grail_ctx* ctx, const grail_seq_elem* elems, con
     if (!ctx) return GRAIL_ERR_INVALID_ARG;
     if (!out_offsets) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "null out_offsets");
     grail_plan* pl = nullptr;
-    int rc = plan_build(ctx, elems, utt_offsets, voices, n_utts, &pl);
+    ElemInput in;
+    in.full = elems;
+    int rc = plan_build(ctx, in, utt_offsets, voices, n_utts, &pl);
     if (rc) return rc;
     // the caller's layout must be the exact counts, packed in utterance order from out_offsets[0]
     for (uint32_t u = 0; u < n_utts; ++u) {
@@ -1177,7 +1294,7 @@ int grail_cuda_stream_new(grail_ctx* ctx, const grail_voice_params* voice, grail
     if (!ctx || !voice || !out_stream) return GRAIL_ERR_INVALID_ARG;
     *out_stream = nullptr;
     const uint32_t offs[2] = { 0, 0 };
-    int rc = validate_inputs(ctx, nullptr, offs, voice, 1);
+    int rc = validate_inputs(ctx, ElemInput(), offs, voice, 1);
     if (rc) return rc;
     grail_stream* s = new (std::nothrow) grail_stream();
     if (!s) return set_err(ctx, GRAIL_ERR_OOM, "host allocation failed");
@@ -1221,7 +1338,9 @@ int grail_cuda_stream_pull(grail_stream* s, float* out, uint64_t max_samples, ui
     ss.finished = s->finished;
     const uint32_t offs[2] = { 0u, (uint32_t)s->pending.size() };
     grail_plan* pl = nullptr;
-    int rc = plan_build(ctx, s->pending.data(), offs, &s->voice, 1, &pl, &ss);
+    ElemInput in;
+    in.full = s->pending.data();
+    int rc = plan_build(ctx, in, offs, &s->voice, 1, &pl, &ss);
     if (rc) return rc;
     const uint64_t n = pl->total_samples;
     if (n == 0) {

@@ -36,6 +36,68 @@ impl Ctx {
     }
 }
 
+/// A batch resident in HBM (`grail_plan`): built once, launched many times.
+pub struct Plan(*mut grail_plan);
+
+impl Plan {
+    /// Sequencer records in (the path's own boundary).
+    pub fn new(ctx: &mut Ctx, elems: &[grail_seq_elem], utt_offsets: &[u32], voices: &[grail_voice_params]) -> Result<Self, i32> {
+        let mut p = std::ptr::null_mut();
+        match unsafe { grail_cuda_plan_create(ctx.0, elems.as_ptr(), utt_offsets.as_ptr(), voices.as_ptr(), voices.len() as u32, &mut p) } {
+            0 => Ok(Plan(p)),
+            e => Err(e),
+        }
+    }
+
+    /// Phoneme ids in: `Intonator` (reference src/lib.rs:1057-1075) and `Selector` (:979-1005) run on the device.
+    /// `storages` holds `n_sounds` records per voice; `utt_storage[u]` picks the voice of utterance `u`.
+    pub fn from_phonemes(ctx: &mut Ctx, phoneme_ids: &[u8], utt_offsets: &[u32], center_frequency: &[f32],
+                         storages: &[grail_elem], n_sounds: u32, utt_storage: Option<&[u32]>,
+                         voices: &[grail_voice_params]) -> Result<Self, i32> {
+        let mut p = std::ptr::null_mut();
+        let rc = unsafe {
+            grail_cuda_plan_create_phonemes(ctx.0, phoneme_ids.as_ptr(), utt_offsets.as_ptr(), center_frequency.as_ptr(),
+                                            storages.as_ptr(), n_sounds, storages.len() as u32 / n_sounds.max(1),
+                                            utt_storage.map_or(std::ptr::null(), |s| s.as_ptr()), voices.as_ptr(),
+                                            voices.len() as u32, &mut p)
+        };
+        if rc == 0 { Ok(Plan(p)) } else { Err(rc) }
+    }
+
+    /// `PhonemeElem` records in (own lengths and pitches): `Selector` runs on the device.
+    pub fn from_phoneme_elems(ctx: &mut Ctx, phonemes: &[grail_phoneme_elem], utt_offsets: &[u32], storages: &[grail_elem],
+                              n_sounds: u32, utt_storage: Option<&[u32]>, voices: &[grail_voice_params]) -> Result<Self, i32> {
+        let mut p = std::ptr::null_mut();
+        let rc = unsafe {
+            grail_cuda_plan_create_phoneme_elems(ctx.0, phonemes.as_ptr(), utt_offsets.as_ptr(), storages.as_ptr(), n_sounds,
+                                                 storages.len() as u32 / n_sounds.max(1),
+                                                 utt_storage.map_or(std::ptr::null(), |s| s.as_ptr()), voices.as_ptr(),
+                                                 voices.len() as u32, &mut p)
+        };
+        if rc == 0 { Ok(Plan(p)) } else { Err(rc) }
+    }
+
+    pub fn total_samples(&self) -> u64 {
+        unsafe { grail_cuda_plan_total_samples(self.0) }
+    }
+
+    /// run the path and copy the packed mono f32 samples to `out` (`total_samples()` entries)
+    pub fn synthesize(&mut self, out: &mut [f32]) -> Result<(), i32> {
+        assert!(out.len() as u64 >= self.total_samples());
+        let mut d = std::ptr::null_mut();
+        let mut rc = unsafe { grail_cuda_plan_device_output(self.0, GRAIL_F32 as i32, &mut d) };
+        if rc == 0 { rc = unsafe { grail_cuda_plan_launch(self.0, d, GRAIL_F32 as i32) }; }
+        if rc == 0 { rc = unsafe { grail_cuda_plan_read_output(self.0, GRAIL_F32 as i32, out.as_mut_ptr() as *mut _) }; }
+        if rc == 0 { Ok(()) } else { Err(rc) }
+    }
+}
+
+impl Drop for Plan {
+    fn drop(&mut self) {
+        unsafe { grail_cuda_plan_destroy(self.0) }
+    }
+}
+
 impl Drop for Ctx {
     fn drop(&mut self) {
         unsafe { grail_cuda_destroy(self.0) }

@@ -123,6 +123,13 @@ class Voice:
     jitter_delta_formant_frequency: np.float32
     jitter_delta_amplitude: np.float32
 
+    def storage(self) -> np.ndarray:
+        """VoiceStorage as grail_elem records indexed by (phoneme id - 3), in make_phonemes! order (src/lib.rs:684-687)"""
+        out = np.zeros(2, _ffi.ELEM_DT)
+        out[0] = self.phonemes.a.to_record()
+        out[1] = self.phonemes.e.to_record()
+        return out
+
     def params(self, jitter_seed: int = 0, synth_seed: int = 0) -> np.ndarray:
         """the grail_voice_params record crossing the C ABI"""
         v = np.zeros((), VOICE_DT)
@@ -227,6 +234,14 @@ class Context:
     def plan(self, elems: np.ndarray, utt_offsets: np.ndarray, voices: np.ndarray) -> "Plan":
         return Plan(self, elems, utt_offsets, voices)
 
+    def plan_phonemes(self, phonemes: np.ndarray, utt_offsets: np.ndarray, storages: np.ndarray, voices: np.ndarray,
+                      center_frequency: Optional[np.ndarray] = None, utt_storage: Optional[np.ndarray] = None) -> "Plan":
+        """phoneme-level input, Selector (and the Intonator stub) on the device.  `phonemes` is either
+        PHONEME_ELEM_DT records (PhonemeElem, src/lib.rs:961-973) or uint8 phoneme ids with one `center_frequency`
+        per utterance; `storages` is [n_storages, n_sounds] grail_elem records (VoiceStorage, :651-659)."""
+        return Plan(self, None, utt_offsets, voices, phonemes=phonemes, storages=storages,
+                    center_frequency=center_frequency, utt_storage=utt_storage)
+
     def stream(self, voice_params: np.ndarray) -> "Stream":
         return Stream(self, voice_params)
 
@@ -234,15 +249,33 @@ class Context:
 class Plan:
     """a batch resident in HBM (grail_plan): upload once, launch many times"""
 
-    def __init__(self, ctx: Context, elems, utt_offsets, voices):
+    def __init__(self, ctx: Context, elems, utt_offsets, voices, phonemes=None, storages=None, center_frequency=None,
+                 utt_storage=None):
         self.ctx = ctx
         self._L = ctx._L
-        e = np.ascontiguousarray(elems, SEQ_ELEM_DT)
         offs = np.ascontiguousarray(utt_offsets, np.uint32)
         v = np.ascontiguousarray(voices, VOICE_DT).reshape(-1)
         self.n_utts = len(offs) - 1
         h = C.c_void_p()
-        ctx._check(self._L.grail_cuda_plan_create(ctx._h, ptr(e), ptr(offs), ptr(v), self.n_utts, C.byref(h)))
+        if phonemes is None:
+            e = np.ascontiguousarray(elems, SEQ_ELEM_DT)
+            ctx._check(self._L.grail_cuda_plan_create(ctx._h, ptr(e), ptr(offs), ptr(v), self.n_utts, C.byref(h)))
+        else:
+            st = np.ascontiguousarray(storages, _ffi.ELEM_DT)
+            st = st.reshape(1, -1) if st.ndim == 1 else st
+            us = None if utt_storage is None else np.ascontiguousarray(utt_storage, np.uint32)
+            ph = np.asarray(phonemes)
+            if ph.dtype == _ffi.PHONEME_ELEM_DT:
+                ph = np.ascontiguousarray(ph)
+                ctx._check(self._L.grail_cuda_plan_create_phoneme_elems(ctx._h, ptr(ph), ptr(offs), ptr(st), st.shape[1],
+                                                                        st.shape[0], ptr(us), ptr(v), self.n_utts, C.byref(h)))
+            else:
+                ids = np.ascontiguousarray(ph, np.uint8)
+                cf = np.ascontiguousarray(center_frequency, np.float32).reshape(-1)
+                if len(cf) != self.n_utts:
+                    raise ValueError("one center_frequency per utterance")
+                ctx._check(self._L.grail_cuda_plan_create_phonemes(ctx._h, ptr(ids), ptr(offs), ptr(cf), ptr(st), st.shape[1],
+                                                                   st.shape[0], ptr(us), ptr(v), self.n_utts, C.byref(h)))
         self._h = h
         self.total_samples = int(self._L.grail_cuda_plan_total_samples(h))
         oo = np.zeros(self.n_utts + 1, np.uint64)

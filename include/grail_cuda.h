@@ -59,6 +59,13 @@ typedef struct grail_seq_elem {
     float      blend_length; /* seconds */
 } grail_seq_elem; /* 208 bytes */
 
+/* PhonemeElem (src/lib.rs:961-973): Selector's input.  frequency is already divided by the sample rate. */
+typedef struct grail_phoneme_elem {
+    uint32_t phoneme;       /* GRAIL_PHONEME_* or GRAIL_PHONEME_FIRST_SOUND + index into the voice storage */
+    float    length, blend_length, frequency;
+} grail_phoneme_elem;       /* 16 bytes */
+enum { GRAIL_PHONEME_SILENCE = 0, GRAIL_PHONEME_STOP = 1, GRAIL_PHONEME_GLIDE = 2, GRAIL_PHONEME_FIRST_SOUND = 3 };
+
 /* The Voice scalars the hot path reads (reference src/lib.rs:696-717) plus the two seeds:
  * jitter_seed is the `seed` argument of .jitter(seed, voice) (src/lib.rs:786); synth_seed is the
  * Synthesize noise seed, which the reference hard-codes to 0 (src/lib.rs:594). */
@@ -134,6 +141,24 @@ int grail_cuda_synthesize_batch(grail_ctx* ctx, const grail_seq_elem* elems, con
 /* ---- resident plans (throughput path: inputs stay in HBM between launches) ------------------ */
 int  grail_cuda_plan_create(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_t* utt_offsets,
                             const grail_voice_params* voices, uint32_t n_utts, grail_plan** out_plan);
+/* ---- phoneme-level input: Selector (src/lib.rs:979-1005) and the Intonator stub (:1057-1075) on the device ----
+ * The step immediately before the path: instead of a 208-byte Sequencer record per phoneme, the caller
+ * sends PhonemeElem records (16 B) or bare phoneme ids (1 B) plus the voice storages they index; the records the
+ * Sequencer reads are written in HBM by a kernel.  Output is bit-identical to expanding on the host and calling
+ * grail_cuda_plan_create.  Phoneme ids follow the reference's enum order (:632-649): 0 Silence, 1 Stop, 2 Glide
+ * (no sound: elem = None), then the sounds of make_phonemes! in declaration order (3 = A, 4 = E, ...);
+ * storages[(s * n_sounds) + (id - 3)] is VoiceStorage field (id - 3) of voice s (:651-659), at the voice's sample
+ * rate; utt_storage[u] picks the voice of utterance u (NULL: all use storage 0). */
+int  grail_cuda_plan_create_phoneme_elems(grail_ctx* ctx, const grail_phoneme_elem* phonemes, const uint32_t* utt_offsets,
+                                          const grail_elem* storages, uint32_t n_sounds, uint32_t n_storages,
+                                          const uint32_t* utt_storage, const grail_voice_params* voices, uint32_t n_utts,
+                                          grail_plan** out_plan);
+/* bare ids: every phoneme gets length 0.5 s, blend 0.5 s and center_frequency[u] (Voice::center_frequency, already
+ * divided by the sample rate) exactly as Intonator::next does today */
+int  grail_cuda_plan_create_phonemes(grail_ctx* ctx, const uint8_t* phoneme_ids, const uint32_t* utt_offsets,
+                                     const float* center_frequency, const grail_elem* storages, uint32_t n_sounds,
+                                     uint32_t n_storages, const uint32_t* utt_storage, const grail_voice_params* voices,
+                                     uint32_t n_utts, grail_plan** out_plan);
 void grail_cuda_plan_destroy(grail_plan* plan);
 uint64_t grail_cuda_plan_total_samples(const grail_plan* plan);
 /* exact per-utterance offsets (n_utts+1 entries) of the plan's packed output */
