@@ -179,3 +179,36 @@ def intonate(phonemes: Iterable[Phoneme], language: Language, voice: Voice) -> I
 
 def select(phoneme_elems: Iterable[PhonemeElem], voice: Voice) -> Selector:
     return Selector(phoneme_elems, voice)
+
+
+def transcribe_batch(texts: Sequence[str], language: Language, leading_silence: bool = True, n_threads: int = 0):
+    """native, multi-threaded Transcriber over a batch of texts (grail_cuda_transcribe_batch; host only).
+    Returns (phoneme ids uint8, utterance offsets uint32) in the layout Context.plan_phonemes takes."""
+    import ctypes as C
+
+    from . import _ffi
+
+    L = _ffi.lib()
+    enc = [t.encode("utf-8") for t in texts]
+    n = len(enc)
+    arr = (C.c_char_p * max(n, 1))(*enc)
+    nbytes = (C.c_size_t * max(n, 1))(*[len(b) for b in enc])
+    rules = (_ffi.TranscriptionRuleC * max(len(language.rules), 1))()
+    keep = []
+    for i, r in enumerate(language.rules):
+        ph = (C.c_uint8 * max(len(r.phonemes), 1))(*[int(p) for p in r.phonemes])
+        keep.append(ph)
+        rules[i].string = r.string.encode("utf-8")
+        rules[i].phonemes = C.cast(ph, C.POINTER(C.c_uint8))
+        rules[i].n_phonemes = len(r.phonemes)
+    offs = np.zeros(n + 1, np.uint32)
+    args = (C.cast(arr, C.c_void_p), C.cast(nbytes, C.c_void_p), n, C.cast(rules, C.c_void_p), len(language.rules),
+            int(language.case_sensitive), int(leading_silence))
+    rc = L.grail_cuda_transcribe_batch(*args, None, 0, _ffi.ptr(offs), n_threads)
+    if rc:
+        raise _ffi.GrailError(rc)
+    ids = np.zeros(int(offs[-1]), np.uint8)
+    rc = L.grail_cuda_transcribe_batch(*args, _ffi.ptr(ids), ids.size, _ffi.ptr(offs), n_threads)
+    if rc:
+        raise _ffi.GrailError(rc)
+    return ids, offs

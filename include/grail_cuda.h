@@ -129,6 +129,25 @@ void grail_cuda_host_free(grail_ctx* ctx, void* ptr);
 int grail_cuda_count_samples(const grail_seq_elem* elems, const uint32_t* utt_offsets,
                              const grail_voice_params* voices, uint32_t n_utts, uint64_t* counts);
 
+/* ---- host text front-end, batched ------------------------------------------------
+ * Transcriber (src/lib.rs:1098-1207): longest-match find-and-replace over a SORTED rule list, one UTF-8 text per
+ * utterance, spread over n_threads host threads (0 = all cores).  Host only, no device needed.
+ * Writes utt_offsets[0..n_texts] (phoneme index of each utterance, the layout grail_cuda_plan_create_phonemes takes)
+ * and, unless ids is NULL (a counting call), the phoneme ids.  leading_silence != 0 starts every text with one
+ * Silence as IntoTranscriber::transcribe does (:1201); 0 is the raw struct the reference's tests build (:1213-1358).
+ * text_bytes may be NULL (NUL-terminated texts).  Errors: GRAIL_ERR_INVALID_ARG (null pointers, unsorted rules, a
+ * rule with an empty string or no phonemes: the reference never terminates on those), GRAIL_ERR_COUNT_MISMATCH
+ * (ids_capacity too small; utt_offsets is valid), GRAIL_ERR_UNSUPPORTED (more than 2^32-1 phonemes). */
+typedef struct grail_transcription_rule {   /* TranscriptionRule, src/lib.rs:1029-1036 */
+    const char*    string;                  /* UTF-8, NUL-terminated */
+    const uint8_t* phonemes;                /* GRAIL_PHONEME_* ids */
+    uint32_t       n_phonemes;
+} grail_transcription_rule;
+int grail_cuda_transcribe_batch(const char* const* texts, const size_t* text_bytes, uint32_t n_texts,
+                                const grail_transcription_rule* rules, uint32_t n_rules, int case_sensitive,
+                                int leading_silence, uint8_t* ids, uint64_t ids_capacity, uint32_t* utt_offsets,
+                                int n_threads);
+
 /* ---- one-shot batch synthesis (the drop-in for draining the iterator chain) ------------------
  * elems / utt_offsets / voices are HOST pointers.  out receives utterance u at
  * out[out_offsets[u] .. out_offsets[u+1]) (mono f32); out_offsets[u+1]-out_offsets[u] must equal

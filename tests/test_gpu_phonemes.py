@@ -102,3 +102,25 @@ def test_phoneme_input_errors(ctx):
                           center_frequency=np.zeros(0, np.float32))
     assert p.total_samples == 0
     p.close()
+
+
+def test_text_to_audio_without_host_records(ctx):
+    """text -> (native batched Transcriber) -> phoneme ids -> (device Intonator + Selector) -> the path, against the
+    reference-shaped chain text.transcribe(..).intonate(..).select(..) expanded on the host (examples/cli.rs:175-184)"""
+    from grail_rs_b200 import text as T
+    v = g.voices.generic()
+    language = T.generic_language()
+    texts = ["a pie i oui e a", "", "ee", "Oui oui", "p"]
+    ids, offs = T.transcribe_batch(texts, language)
+    vp = np.zeros(len(texts), g.VOICE_DT)
+    vp[:] = v.params(0)
+    vp["jitter_seed"] = np.arange(len(texts))
+    cf = np.full(len(texts), v.center_frequency, np.float32)
+    got, goo = _run(ctx.plan_phonemes(ids, offs, v.storage(), vp, center_frequency=cf))
+    host = [g.pack_sequence(list(T.transcribe(t, language).intonate(language, v).select(v))) for t in texts]
+    elems = np.concatenate(host)
+    hoffs = np.concatenate([[0], np.cumsum([len(h) for h in host])]).astype(np.uint32)
+    assert np.array_equal(hoffs, offs)
+    want, woo = _run(ctx.plan(elems, hoffs, vp))
+    assert np.array_equal(goo, woo)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
