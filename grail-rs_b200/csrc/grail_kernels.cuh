@@ -1186,7 +1186,7 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
     // Jitter perturbation (:764-773), exp_approx (:75-82) and the SVF coefficients (:555-562).
     // lp = 1 - exp_approx(smooth); turbulence and amplitude are folded: v0 = a * (amp0 + amp1 * noise) with
     // amp0 = amp (1 - turb), amp1 = amp turb   (1 * (1 - turb) + noise * turb, times amp: :544-550)
-    struct Coef { float a1, a2, a3, lp, amp0, amp1, br; };
+    struct Coef { float a1, g, lp, amp0, amp1, br; };
     auto coeffs = [&](const FormantLane& F, float alpha, float jp) -> Coef {
         Coef c;
         const float ff = fmaf(jp, F.ff2, fmaf(alpha, F.ff1, F.ff0));
@@ -1204,8 +1204,7 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
         const float g = num * frcp(den);
         const float kq = bw * frcp(ff);
         c.a1 = frcp(fmaf(g, g + kq, 1.0f));
-        c.a2 = g * c.a1;
-        c.a3 = g * c.a2;
+        c.g = g;
         return c;
     };
     // One filter step of one formant (:531-571): breath mix, one-pole low-pass, turbulence, amplitude, SVF tick.
@@ -1214,8 +1213,8 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
         F.a = fmaf(c.lp, nw - F.a, F.a);                                      // :538
         const float v0 = F.a * fmaf(c.amp1, nz, c.amp0);                      // :544-550
         const float v3 = v0 - F.c;                                            // :565
-        const float v1 = fmaf(c.a1, F.b, c.a2 * v3);
-        const float v2 = fmaf(c.a3, v3, fmaf(c.a2, F.b, F.c));
+        const float v1 = c.a1 * fmaf(c.g, v3, F.b);                           // a1 b + a2 v3 with a2 = g a1  (:561, :566)
+        const float v2 = fmaf(c.g, v1, F.c);                                  // c + a2 b + a3 v3 with a3 = g a2  (:562, :567)
         F.b = fmaf(2.0f, v1, -F.b);
         F.c = fmaf(2.0f, v2, -F.c);
         return v1;
@@ -1299,7 +1298,7 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
     Coef cend[FPT];        // coefficients at the current clock values (the next block's start point)
     bool c_valid = false;
 #pragma unroll
-    for (int j = 0; j < FPT; ++j) cend[j] = Coef{ 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+    for (int j = 0; j < FPT; ++j) cend[j] = Coef{ 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
 
     // ---- one loop over [-wmax, lmax) in steps of 8: warm-up (r < 0, no output) then the chunk itself
     for (int r = -(int)wmax; r < (int)lmax; r += 8) {
@@ -1339,7 +1338,7 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
                     for (int j = 0; j < FPT; ++j) {
                         c0[j] = cend[j];
                         cend[j] = coeffs(L[j], alpha, jph);
-                        dc[j].a1 = cend[j].a1 - c0[j].a1; dc[j].a2 = cend[j].a2 - c0[j].a2; dc[j].a3 = cend[j].a3 - c0[j].a3;
+                        dc[j].a1 = cend[j].a1 - c0[j].a1; dc[j].g = cend[j].g - c0[j].g;
                         dc[j].lp = cend[j].lp - c0[j].lp; dc[j].amp0 = cend[j].amp0 - c0[j].amp0;
                         dc[j].amp1 = cend[j].amp1 - c0[j].amp1; dc[j].br = cend[j].br - c0[j].br;
                     }
@@ -1354,7 +1353,7 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
 #pragma unroll
                     for (int j = 0; j < FPT; ++j) {
                         Coef c;
-                        c.a1 = fmaf(dc[j].a1, t, c0[j].a1); c.a2 = fmaf(dc[j].a2, t, c0[j].a2); c.a3 = fmaf(dc[j].a3, t, c0[j].a3);
+                        c.a1 = fmaf(dc[j].a1, t, c0[j].a1); c.g = fmaf(dc[j].g, t, c0[j].g);
                         c.lp = fmaf(dc[j].lp, t, c0[j].lp); c.amp0 = fmaf(dc[j].amp0, t, c0[j].amp0);
                         c.amp1 = fmaf(dc[j].amp1, t, c0[j].amp1); c.br = fmaf(dc[j].br, t, c0[j].br);
                         acc += tick(L[j], c, s8[k], d1, nz);
