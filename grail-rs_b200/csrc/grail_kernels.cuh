@@ -30,9 +30,10 @@ struct UttDev {
     uint32_t elem_first, n_elems;  // phonemes of this utterance in `elems` / `segs`
     uint32_t n_samples;
     uint32_t jit_sched;            // index into JitSchedDev
-    uint32_t item_first, n_items;  // work items (time chunks) of this utterance, consecutive
+    uint32_t item_first, n_items;  // work items (time chunks) of this utterance: item_first + c * item_stride
     uint32_t n_active;             // number of formants whose amplitude is not identically zero
     uint8_t  active[8];            // their indices, ascending
+    uint32_t item_stride;          // 1, or 32 when 32 equally long utterances are interleaved chunk by chunk
     uint64_t out_off;              // first output sample
     uint64_t f_off;                // first entry in the linear F_t scratch (multiple of 8)
     grail_voice_params voice;
@@ -578,7 +579,7 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
                 }
             }
             dst_j += PH_TILE;
-            if (dst_j >= CL) { dst_j -= CL; ++dst_item; }
+            if (dst_j >= CL) { dst_j -= CL; dst_item += U.item_stride; }
         }
     }
 }
@@ -934,7 +935,7 @@ __global__ void k_ps_saw(PScanDev S, PlanDev P, uint32_t utt)
         }
     }
     const uint32_t CL = P.chunk_len;
-    const uint32_t item = U.item_first + (uint32_t)(b0 / CL), j = (uint32_t)(b0 % CL);
+    const uint32_t item = U.item_first + (uint32_t)(b0 / CL) * U.item_stride, j = (uint32_t)(b0 % CL);
     float4* dst = reinterpret_cast<float4*>(P.saw + saw_index(item, j, CL));
     dst[0] = make_float4(s[0], s[1], s[2], s[3]);
     dst[1] = make_float4(s[4], s[5], s[6], s[7]);
@@ -1272,7 +1273,8 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
 
     // saw source: walks the tiled layout from sample ns; crossing into the next chunk of the utterance (and,
     // at r == 0, into this lane's own chunk) is a pointer reset every CL samples
-    uint32_t src_item = U.item_first + ns / CL, src_j = ns % CL;
+    const uint32_t item_stride = U.item_stride;
+    uint32_t src_item = U.item_first + (ns / CL) * item_stride, src_j = ns % CL;
     const float4* sp = reinterpret_cast<const float4*>(P.saw + saw_index(src_item, src_j, CL));
     // saw values are fetched one iteration ahead (register double buffer) so the L2 latency of the
     // coalesced 128-bit loads is covered by a whole block of arithmetic
@@ -1283,7 +1285,7 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
         src_j += 8;
         if (src_j == CL) {
             src_j = 0;
-            ++src_item;
+            src_item += item_stride;
             sp = reinterpret_cast<const float4*>(P.saw + saw_index(src_item, 0, CL));
         } else {
             sp += 64;

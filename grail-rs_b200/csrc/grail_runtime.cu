@@ -44,6 +44,7 @@ struct grail_ctx {
     uint32_t max_chunk = 1u << 22;
     int      debug_taps = 0;
     uint32_t pscan_min = 1u << 18;   // utterances at least this long may get the exact parallel phase scan
+    int interleave = 1;              // interleave equally long utterances chunk by chunk in k_formant's CTAs
     int pscan_cost_model = 1;        // 0: scan every utterance >= pscan_min (at most 16), whatever it costs
     int      zero_copy_out = 0;      // 1: k_formant stores straight into pinned host output (measured slower: 23 vs 50 GB/s over PCIe)
     int      formants_per_lane = 2;  // 1 or 2 formants of an utterance share one lane's clocks, noise and saw
@@ -558,15 +559,46 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
     for (uint32_t u = 0; u < n_utts; ++u) order[u] = u;
     std::stable_sort(order.begin(), order.end(),
                      [&](uint32_t a, uint32_t b) { return pl->utts[a].n_samples > pl->utts[b].n_samples; });
-    for (uint32_t u : order) {
-        UttDev& U = pl->utts[u];
+    // A CTA of k_formant is 32 consecutive items.  When 32 neighbours in this order have the same number of chunks
+    // they are interleaved chunk by chunk (item = first + c * 32): a CTA then holds the SAME chunk of 32 utterances,
+    // so with a shared voice the value-noise wraps, alpha clips and phoneme hand-overs fall on the same samples in
+    // every lane and the warp leaves its interpolating fast path 32 times less often.  Otherwise: consecutive.
+    auto chunks_of = [&](uint32_t u) { return (pl->utts[u].n_samples + pl->chunk_len - 1) / pl->chunk_len; };
+    for (size_t o0 = 0; o0 < order.size();) {
+        bool same = ctx->interleave && o0 + 32 <= order.size() && chunks_of(order[o0]) > 0;
+        for (size_t k = 1; same && k < 32; ++k) same = chunks_of(order[o0 + k]) == chunks_of(order[o0]);
+        if (same) {
+            while (pl->items.size() & 31u) {             // start on a CTA boundary: empty items (idle lanes)
+                ItemDev pad;
+                pad.utt = order[o0]; pad.n0 = 0; pad.len = 0; pad.pad = 0;
+                pl->items.push_back(pad);
+            }
+            const uint32_t base = (uint32_t)pl->items.size(), nc = chunks_of(order[o0]);
+            for (uint32_t c = 0; c < nc; ++c)
+                for (uint32_t k = 0; k < 32; ++k) {
+                    UttDev& U = pl->utts[order[o0 + k]];
+                    const uint32_t n0 = c * pl->chunk_len;
+                    ItemDev it;
+                    it.utt = order[o0 + k]; it.n0 = n0; it.len = std::min(pl->chunk_len, U.n_samples - n0); it.pad = 0;
+                    pl->items.push_back(it);
+                }
+            for (uint32_t k = 0; k < 32; ++k) {
+                UttDev& U = pl->utts[order[o0 + k]];
+                U.item_first = base + k; U.item_stride = 32; U.n_items = nc;
+            }
+            o0 += 32;
+            continue;
+        }
+        UttDev& U = pl->utts[order[o0]];
         U.item_first = (uint32_t)pl->items.size();
+        U.item_stride = 1;
         for (uint32_t n0 = 0; n0 < U.n_samples; n0 += pl->chunk_len) {
             ItemDev it;
-            it.utt = u; it.n0 = n0; it.len = std::min(pl->chunk_len, U.n_samples - n0); it.pad = 0;
+            it.utt = order[o0]; it.n0 = n0; it.len = std::min(pl->chunk_len, U.n_samples - n0); it.pad = 0;
             pl->items.push_back(it);
         }
         U.n_items = (uint32_t)pl->items.size() - U.item_first;
+        ++o0;
     }
     pl->n_items = (uint32_t)pl->items.size();
     pl->n_groups = (pl->n_items + 31) / 32;
@@ -961,6 +993,8 @@ int grail_cuda_set_option(grail_ctx* ctx, const char* key, double value)
         ctx->formants_per_lane = (int)value;
     } else if (!strcmp(key, "pipeline")) {
         ctx->pipeline = value != 0.0;
+    } else if (!strcmp(key, "interleave")) {
+        ctx->interleave = value != 0.0;
     } else if (!strcmp(key, "pscan_cost_model")) {
         ctx->pscan_cost_model = value != 0.0;
     } else if (!strcmp(key, "pscan_min_samples")) {
@@ -1210,7 +1244,7 @@ int grail_cuda_plan_read_intermediates(grail_plan* plan, float* frequency, float
         for (uint32_t u = 0; u < plan->n_utts; ++u) {
             const UttDev& U = plan->utts[u];
             for (uint32_t n = 0; n < U.n_samples; ++n) {
-                const uint32_t item = U.item_first + n / CL, j = n % CL;
+                const uint32_t item = U.item_first + (n / CL) * U.item_stride, j = n % CL;
                 const size_t idx = ((size_t)(item >> 5) * (CL >> 3) + (j >> 3)) * 256u + (item & 31u) * 8u + (j & 7u);
                 saw[U.out_off + n] = tmp[idx];
             }
