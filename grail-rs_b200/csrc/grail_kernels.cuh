@@ -1059,7 +1059,7 @@ struct FormantLane {
 };
 
 template <int FPT> struct FormantCfg { static constexpr int warps_per_sm = 24; };   // 80 registers per lane
-template <> struct FormantCfg<2> { static constexpr int warps_per_sm = 16; };       // 128 registers per lane
+template <> struct FormantCfg<2> { static constexpr int warps_per_sm = 12; };       // up to 168 registers per lane
 
 template <int NW, int FPT>
 __global__ void __launch_bounds__(NW * 32, FormantCfg<FPT>::warps_per_sm / NW)
@@ -1093,7 +1093,7 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
     const float jinc = U.voice.jitter_frequency;
     const float dff = U.voice.jitter_delta_formant_frequency;
     const float hda = 0.5f * U.voice.jitter_delta_amplitude;   // :769
-    const float quiet_t = 9.0f * dt, quiet_j = 1.0f - 9.0f * jinc;
+    const float quiet_t = 17.0f * dt, quiet_j = 1.0f - 17.0f * jinc;   // no hand-over / wrap within the next 16 samples
     const uint32_t jseed = U.voice.jitter_seed;
 
     FormantLane L[FPT];
@@ -1122,7 +1122,8 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
     uint32_t wmax = wlen;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    const uint32_t wmine = min(wmax, it.n0);      // multiple of 8 (n0 is a multiple of 256)
+    wmax = (wmax + 15u) & ~15u;                   // whole 16-sample interpolation blocks
+    const uint32_t wmine = min(wmax, it.n0);      // multiple of 16 (n0 is a multiple of 256)
     const uint32_t ns = it.n0 - wmine;            // first sample this lane computes
 
     // ---- shared (per lane) clocks and noise at sample ns
@@ -1302,39 +1303,46 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
 #pragma unroll
     for (int j = 0; j < FPT; ++j) cend[j] = Coef{ 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
 
-    // ---- one loop over [-wmax, lmax) in steps of 8: warm-up (r < 0, no output) then the chunk itself
-    for (int r = -(int)wmax; r < (int)lmax; r += 8) {
+    // ---- one loop over [-wmax, lmax) in steps of 8: warm-up (r < 0, no output) then the chunk itself.
+    // Blocks of 16 samples (two iterations, half = 0 / 1) are classified once, at their first half.
+    // hand: a phoneme hand-over may fall inside (per lane, rare: generic per-sample loop).
+    // exact: a value-noise wrap or the alpha clip falls inside, so the parameters have a kink in this block; if
+    // ANY lane of the warp is in that class the whole warp takes the exact per-sample path (a uniform branch).
+    // Otherwise every parameter is linear in time over the block and the 6 per-sample coefficients are
+    // interpolated between the block's end points (error ~ h^2/8 c'' < 1e-7 relative, the size of f32 rounding),
+    // which removes the blend / tan_approx / reciprocal work from 15 of every 16 samples.
+    // (the ragged last block of a chunk also goes through the per-sample loop, so that the lane stops exactly
+    //  after its last sample: a continued stream picks the filter states up from there)
+    Coef c0[FPT], dc[FPT];
+#pragma unroll
+    for (int j = 0; j < FPT; ++j) { c0[j] = cend[j]; dc[j] = cend[j]; }
+    bool hand = false, warp_exact = false;
+    int half = 0;
+    for (int r = -(int)wmax; r < (int)lmax; r += 8, half ^= 1) {
         const bool act = r >= r_lo && r < r_hi;
         const float4 sa = na, sb = nb;
         if (r + 8 >= r_lo && r + 8 < r_hi) fetch();
         float v[8];
-        // Block classes.  hand: a phoneme hand-over may fall inside (per lane, rare: generic per-sample loop).
-        // exact: a value-noise wrap or the alpha clip falls inside, so the parameters have a kink in this block; if
-        // ANY lane of the warp is in that class the whole warp takes the exact per-sample path (a uniform branch).
-        // Otherwise every parameter is linear in time over the block and the 7 per-sample coefficients are
-        // interpolated between the block's end points (error ~ h^2/8 c'' ~ 1e-9 relative, far below f32 rounding),
-        // which removes the blend / tan_approx / reciprocal work from 7 of every 8 samples.
-        // (the ragged last block of a chunk also goes through the per-sample loop, so that the lane stops exactly
-        //  after its last sample: a continued stream picks the filter states up from there)
-        const bool hand = act && (!(time > quiet_t) || r + 8 > r_hi);
-        const float a_now = time * inv_bl, a_end = fmaf(8.0f, ndt, time) * inv_bl;
-        const bool kink = act && !hand && (!(jph < quiet_j) || ((a_now > 1.0f) != (a_end > 1.0f)));
-        const bool warp_exact = __any_sync(0xffffffffu, kink);
+        if (half == 0) {
+            hand = act && (!(time > quiet_t) || r + 16 > r_hi);
+            const float a_now = time * inv_bl, a_end = fmaf(16.0f, ndt, time) * inv_bl;
+            const bool kink = act && !hand && (!(jph < quiet_j) || ((a_now > 1.0f) != (a_end > 1.0f)));
+            warp_exact = __any_sync(0xffffffffu, kink);
+        }
         if (act) {
             if (!hand && !warp_exact) {
                 const float s8[8] = { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w };
-                Coef c0[FPT], dc[FPT];
-                if (!c_valid) {
-                    const float alpha = fminf(time * inv_bl, 1.0f);
+                if (half == 0) {
+                    if (!c_valid) {
+                        const float alpha = fminf(time * inv_bl, 1.0f);
 #pragma unroll
-                    for (int j = 0; j < FPT; ++j) cend[j] = coeffs(L[j], alpha, jph);
-                }
+                        for (int j = 0; j < FPT; ++j) cend[j] = coeffs(L[j], alpha, jph);
+                    }
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {       // the clocks stay literal f32 chains  (:861, :291)
-                    time = __fadd_rn(time, ndt);
-                    jph = __fadd_rn(jph, jinc);
-                }
-                {
+                    for (int k = 0; k < 16; ++k) {  // the clocks stay literal f32 chains  (:861, :291)
+                        time = __fadd_rn(time, ndt);
+                        jph = __fadd_rn(jph, jinc);
+                    }
                     const float alpha = fminf(time * inv_bl, 1.0f);
 #pragma unroll
                     for (int j = 0; j < FPT; ++j) {
@@ -1344,13 +1352,20 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
                         dc[j].lp = cend[j].lp - c0[j].lp; dc[j].amp0 = cend[j].amp0 - c0[j].amp0;
                         dc[j].amp1 = cend[j].amp1 - c0[j].amp1; dc[j].br = cend[j].br - c0[j].br;
                     }
+                    c_valid = true;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < FPT; ++j) {     // second half: start from the block's midpoint
+                        c0[j].a1 = fmaf(dc[j].a1, 0.5f, c0[j].a1); c0[j].g = fmaf(dc[j].g, 0.5f, c0[j].g);
+                        c0[j].lp = fmaf(dc[j].lp, 0.5f, c0[j].lp); c0[j].amp0 = fmaf(dc[j].amp0, 0.5f, c0[j].amp0);
+                        c0[j].amp1 = fmaf(dc[j].amp1, 0.5f, c0[j].amp1); c0[j].br = fmaf(dc[j].br, 0.5f, c0[j].br);
+                    }
                 }
-                c_valid = true;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     float d1, nz;
                     noise(s8[k], d1, nz);
-                    const float t = (float)k * 0.125f;
+                    const float t = (float)k * 0.0625f;
                     float acc = 0.0f;
 #pragma unroll
                     for (int j = 0; j < FPT; ++j) {

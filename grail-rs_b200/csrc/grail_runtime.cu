@@ -525,10 +525,11 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
             const int reserve = (32768 + cta_regs - 1) / cta_regs;
             occ = std::max(occ - reserve, (occ + 1) / 2);
         } else {
-            // Fewer, longer chunks beat full occupancy (the warm-up is paid per chunk): aim at ~3/4 of the resident
-            // CTAs, and keep the warps per SM a multiple of 4 so the four sub-partitions stay evenly loaded
-            // (measured at config 2, FPT = 2: 6 CTAs/SM 2.13 ms, 8 -> 2.23 ms, 5 / 7 -> 2.37 / 2.40 ms).
-            int c = std::max(1, (3 * occ) / 4);
+            // Fewer, longer chunks beat full occupancy (the warm-up is paid per chunk): aim at 12 warps per SM with two
+            // formants per lane (what 167 registers allow; measured at config 2: 6 CTAs/SM 1.69 ms, 5 -> 1.91, 4 -> 1.78)
+            // and 3/4 of the resident warps with one, and keep the warps per SM a multiple of 4 so the four
+            // sub-partitions stay evenly loaded.
+            int c = pl->fpt == 2 ? std::min(occ, std::max(1, 12 / (int)nw)) : std::max(1, (3 * occ) / 4);
             while (c > 1 && ((c * (int)nw) % 4) != 0) --c;
             occ = c;
         }
