@@ -180,8 +180,26 @@ __global__ void k_jitter_schedule(PlanDev P)
 struct FreqSeg {
     float xf, yf;   // blend endpoints: out = xf*(1-alpha) + yf*alpha
     float blend_len;
+    float rcp_bl;   // RN(1 / blend_len) when the fast exact division applies, else 0
     int   silent;   // both cur and next have no element: SynthesisElem::silent(), frequency 0.25
 };
+
+// RN(a / b) for many a and one b.  With y = RN(1/b) (correctly rounded), q = RN(a y), r = a - b q (exact in an FMA),
+// RN(q + r y) is the correctly rounded quotient (Markstein 1990) as long as nothing under- or overflows on the way;
+// the guard keeps a and b far inside the normal range and everything else goes through the IEEE division.
+__device__ __forceinline__ float div_by_const(float a, float b, float y)
+{
+    if (y != 0.0f && a > 1e-25f && a < 1e25f) {
+        const float q = __fmul_rn(a, y);
+        const float r = __fmaf_rn(-b, q, a);
+        return __fmaf_rn(r, y, q);
+    }
+    return sdiv(a, b);
+}
+__device__ __forceinline__ float div_const_rcp(float b)
+{
+    return (b > 1e-12f && b < 1e12f) ? __frcp_rn(b) : 0.0f;
+}
 
 __device__ __forceinline__ FreqSeg load_freq_seg(const float* ue, uint32_t p, uint32_t n_elems)
 {
@@ -192,6 +210,7 @@ __device__ __forceinline__ FreqSeg load_freq_seg(const float* ue, uint32_t p, ui
     if (p + 1 < n_elems) c_on = __float_as_uint(nxt[SE_HAS]) != 0u;
     FreqSeg s;
     s.blend_len = cur[SE_BLEND];
+    s.rcp_bl = div_const_rcp(s.blend_len);
     s.silent = 0;
     if (b_on && c_on) { s.xf = nxt[SE_FREQ]; s.yf = cur[SE_FREQ]; }      // c.blend(b, alpha)          :902
     else if (b_on)    { s.xf = cur[SE_FREQ]; s.yf = cur[SE_FREQ]; }      // b.copy_silent().blend(b)   :911
@@ -205,10 +224,13 @@ __device__ __forceinline__ FreqSeg load_freq_seg(const float* ue, uint32_t p, ui
 // closed form at the run start, then replayed literally; the scalar frequency path uses strict ops in
 // the reference's order (blend :406, value-noise lerp :254, jitter add :763).
 // ------------------------------------------------------------------------------------------------
-constexpr int FREQ_RUN = 512;   // samples per lane: amortises the two closed-form clock fast-forwards
+constexpr int FREQ_RUN = 256;   // samples per lane: amortises the two closed-form clock fast-forwards; short enough that
+                                // the last partial wave stays small (measured 512 / 256 / 128: 0.41 / 0.36 / 0.40 ms)
 
 __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_item)
 {
+    // lanes of a warp = consecutive runs of one item (measured against "the same run of 32 consecutive items", which
+    // lines events up across lanes but scatters every per-utterance load: 0.36 vs 0.39 ms at config 2)
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t item = (uint32_t)(t / runs_per_item);
     const uint32_t run = (uint32_t)(t % runs_per_item);
@@ -249,7 +271,7 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
         if (seg.silent) {
             fb = 0.25f;
         } else {
-            const float alpha = fminf(sdiv(time, seg.blend_len), 1.0f);                    // :899
+            const float alpha = fminf(div_by_const(time, seg.blend_len, seg.rcp_bl), 1.0f);   // :899
             fb = sadd(smul(seg.xf, ssub(1.0f, alpha)), smul(seg.yf, alpha));               // :406
         }
         const float n0 = sadd(smul(cur, ssub(1.0f, jph)), smul(nxt, jph));                 // :254

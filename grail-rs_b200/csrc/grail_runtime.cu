@@ -806,7 +806,7 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
     CU(ctx, cudaEventRecord(ev[1], s));
     if (pl->n_items) {
         const uint32_t runs = (pl->chunk_len + FREQ_RUN - 1) / FREQ_RUN;
-        const uint64_t threads = (uint64_t)pl->n_items * runs;
+        const uint64_t threads = (uint64_t)pl->n_groups * 32ull * runs;
         k_frequency<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(P, runs);
         pl->last_launches++;
     }
