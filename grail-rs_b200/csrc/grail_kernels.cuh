@@ -406,6 +406,15 @@ __device__ __noinline__ float saw_edge(float phase, float f)
     return ssub(ssub(smul(2.0f, phase), 1.0f), polyblep);        // :517
 }
 
+// (x >= 1) ? 1.0f : 0.0f as a float-valued compare: keeps the wrap off the predicate path, whose 13-cycle latency
+// would otherwise sit on every step of the literal chain (a negative or NaN x gives 0)
+__device__ __forceinline__ float ge_one(float x)
+{
+    float r;
+    asm("set.ge.f32.f32 %0, %1, 0f3F800000;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // 8 steps exactly as the reference takes them (any increment, any wrap)  :520-525
 __device__ __forceinline__ float phase_steps8(float phase, const float4& fa, const float4& fb, uint32_t valid)
 {
@@ -414,7 +423,7 @@ __device__ __forceinline__ float phase_steps8(float phase, const float4& fa, con
     for (int k = 0; k < 8; ++k) {
         if ((uint32_t)k < valid) {
             phase = sadd(phase, fv[k]);
-            if (phase >= 1.0f) phase = ssub(phase, 1.0f);
+            phase = ssub(phase, ge_one(phase));     // if phase >= 1 { phase -= 1 }: x - 0.0 is x, bit for bit (x >= +0 or NaN)
         }
     }
     return phase;
@@ -428,24 +437,36 @@ __device__ __forceinline__ float phase_steps8(float phase, const float4& fa, con
 __device__ __noinline__ float phase_redo_quad(float ps0, float ps1, float ps2, float ps3, float ps4, unsigned f_a,
                                               unsigned p_a, bool lane0)
 {
-    const float pe[5] = { ps0, ps1, ps2, ps3, ps4 };
-    int b = 0;
+    // all 32 increments up front: eight loads in flight while the wrap block is located
+    float4 f[8];
 #pragma unroll
-    for (int i = 1; i <= 3; ++i) b += (pe[i] < 1.0f) ? 1 : 0;     // monotone: number of leading blocks that end below 1.0
-    float phase = b == 0 ? ps0 : (b == 1 ? ps1 : (b == 2 ? ps2 : ps3));
-    if (lane0) sts128(p_a, ps0, ps1, ps2, ps3);                   // entries past b are overwritten below
-    {
-        const float4 fa = lds128(f_a + b * 32), fb = lds128(f_a + b * 32 + 16);
-        phase = phase_steps8(phase, fa, fb, 8);
+    for (int i = 0; i < 8; ++i) f[i] = lds128(f_a + i * 16);
+    // blocks 0..b-1 end below 1.0 (the chain is monotone): their start phases stand; block b holds the wrap
+    const int b = (ps1 < 1.0f ? 1 : 0) + (ps2 < 1.0f ? 1 : 0) + (ps3 < 1.0f ? 1 : 0);
+    float phase, s1 = ps1, s2 = ps2, s3 = ps3;
+    // one plain block after the wrap: speculate again, literal steps only if a second wrap follows at once
+    auto next_block = [&](float ph, const float4& a, const float4& c) -> float {
+        const float p4 = sadd(sadd(sadd(sadd(ph, a.x), a.y), a.z), a.w);
+        const float p8 = sadd(sadd(sadd(sadd(p4, c.x), c.y), c.z), c.w);
+        return (p8 < 1.0f) ? p8 : phase_steps8(ph, a, c, 8);
+    };
+    if (b == 0) {
+        s1 = phase_steps8(ps0, f[0], f[1], 8);
+        s2 = next_block(s1, f[2], f[3]);
+        s3 = next_block(s2, f[4], f[5]);
+        phase = next_block(s3, f[6], f[7]);
+    } else if (b == 1) {
+        s2 = phase_steps8(ps1, f[2], f[3], 8);
+        s3 = next_block(s2, f[4], f[5]);
+        phase = next_block(s3, f[6], f[7]);
+    } else if (b == 2) {
+        s3 = phase_steps8(ps2, f[4], f[5], 8);
+        phase = next_block(s3, f[6], f[7]);
+    } else {
+        phase = phase_steps8(ps3, f[6], f[7], 8);
     }
-#pragma unroll 1
-    for (++b; b < 4; ++b) {
-        const float4 fa = lds128(f_a + b * 32), fb = lds128(f_a + b * 32 + 16);
-        if (lane0) sts32(p_a + b * 4, phase);
-        const float p4 = sadd(sadd(sadd(sadd(phase, fa.x), fa.y), fa.z), fa.w);
-        const float p8 = sadd(sadd(sadd(sadd(p4, fb.x), fb.y), fb.z), fb.w);
-        phase = (p8 < 1.0f) ? p8 : phase_steps8(phase, fa, fb, 8);
-    }
+    if (lane0) sts128(p_a, ps0, s1, s2, s3);
+    (void)ps4;
     return phase;
 }
 
