@@ -41,7 +41,7 @@ FLOPS_PER_SAMPLE = 762
 FLOPS_PER_SAMPLE_FORMANT = 736
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_formant launch on this workload, from the committed
 # `ncu --set full` capture (profiles/r1_k_formant_ncu_full.txt: 1.567 GB read + 0.868 GB written; algorithmic 1.806 GB)
-NCU_TRAFFIC_BYTES = 1566748000 + 867958528
+NCU_TRAFFIC_BYTES = 1373341000 + 861585152
 
 
 def host_cores() -> int:
@@ -266,9 +266,10 @@ def run_ours(args):
             "peak_source": "FFMA issue-rate probe measured live in this run (MEASURED_PEAKS.json has no fp32 figure)",
             "flops_per_sample": FLOPS_PER_SAMPLE_FORMANT, "launch_ms": formant_ms,
             "note": "achieved counts the reference's as-written flops (SURVEY 8d); the kernel executes fewer: 4 of the "
-                    "8 formants of the default voice are exactly zero and are skipped, and the 7 per-sample filter "
-                    "coefficients are interpolated between exact 8-sample end points, so frac can exceed 1; ncu "
-                    "(profiles/r1_k_formant_ncu_full.txt) reads 64 % issue-slot utilisation",
+                    "8 formants of the default voice are exactly zero and are skipped, and the 6 per-sample filter "
+                    "coefficients are interpolated between exact 16-sample end points, so frac exceeds 1; the honest "
+                    "efficiency figure is ncu's (profiles/r1_k_formant_ncu_full.txt): 1.18e9 warp instructions per "
+                    "launch, 63 % of the issue slots busy",
             "mufu_peak_per_s": probe["mufu_ops"],
             "hbm": {"achieved": hbm_bytes / (formant_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                     "frac": (hbm_bytes / (formant_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
