@@ -1155,17 +1155,24 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
         L[j].a = L[j].b = L[j].c = 0.f;
     }
 
-    // ---- warm-up depth: per lane (max over its formants), then the warp maximum so the warp walks the same rows
-    uint32_t wlen = 0;
-    if (on && it.n0 > 0) {
+    // ---- warm-up depth: per formant slot, maximised over the warp so the warp walks the same rows.  The slot with the
+    // longer warm-up goes first: the other one (FPT = 2) joins only `w1` rows before the chunk, so the rows before
+    // that run one formant instead of two (formant 0 of the default voice needs 3 590 samples, formant 1 1 600).
+    uint32_t wslot[FPT];
 #pragma unroll
-        for (int j = 0; j < FPT; ++j)
-            if (L[j].fi >= 0) wlen = max(wlen, warmup_len(ue, segs, n_elems, it.n0, L[j].fi, dff, P.warmup_nepers));
+    for (int j = 0; j < FPT; ++j) {
+        uint32_t wl = 0;
+        if (on && it.n0 > 0 && L[j].fi >= 0) wl = warmup_len(ue, segs, n_elems, it.n0, L[j].fi, dff, P.warmup_nepers);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wl = max(wl, __shfl_xor_sync(0xffffffffu, wl, o));
+        wslot[j] = (wl + 15u) & ~15u;             // whole 16-sample interpolation blocks
     }
-    uint32_t wmax = wlen;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    wmax = (wmax + 15u) & ~15u;                   // whole 16-sample interpolation blocks
+    if (FPT == 2 && wslot[FPT - 1] > wslot[0]) {  // warp-uniform
+        const int f = L[0].fi; L[0].fi = L[FPT - 1].fi; L[FPT - 1].fi = f;
+        const uint32_t t = wslot[0]; wslot[0] = wslot[FPT - 1]; wslot[FPT - 1] = t;
+    }
+    const uint32_t wmax = wslot[0];
+    const int r_join = (FPT == 2) ? -(int)wslot[FPT - 1] : (int)0x80000000;   // first row of the second slot
     const uint32_t wmine = min(wmax, it.n0);      // multiple of 16 (n0 is a multiple of 256)
     const uint32_t ns = it.n0 - wmine;            // first sample this lane computes
 
@@ -1372,54 +1379,65 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
             const bool kink = act && !hand && (!(jph < quiet_j) || ((a_now > 1.0f) != (a_end > 1.0f)));
             warp_exact = __any_sync(0xffffffffu, kink);
         }
+        if (FPT == 2 && r == r_join && r_join != -(int)wmax) {
+            // the second slot starts here, from rest (whatever the exact / hand-over rows before may have left in it)
+            if (act) { L[FPT - 1].a = 0.f; L[FPT - 1].b = 0.f; L[FPT - 1].c = 0.f; }
+            c_valid = false;
+        }
         if (act) {
             if (!hand && !warp_exact) {
                 const float s8[8] = { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w };
-                if (half == 0) {
-                    if (!c_valid) {
+                // NJ = number of slots that run in this block (a compile-time constant in each instantiation)
+                auto interp_block = [&](auto nj_tag) {
+                    constexpr int NJ = decltype(nj_tag)::value;
+                    if (half == 0) {
+                        if (!c_valid) {
+                            const float alpha = fminf(time * inv_bl, 1.0f);
+#pragma unroll
+                            for (int j = 0; j < NJ; ++j) cend[j] = coeffs(L[j], alpha, jph);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {  // the clocks stay literal f32 chains  (:861, :291)
+                            time = __fadd_rn(time, ndt);
+                            jph = __fadd_rn(jph, jinc);
+                        }
                         const float alpha = fminf(time * inv_bl, 1.0f);
 #pragma unroll
-                        for (int j = 0; j < FPT; ++j) cend[j] = coeffs(L[j], alpha, jph);
+                        for (int j = 0; j < NJ; ++j) {
+                            c0[j] = cend[j];
+                            cend[j] = coeffs(L[j], alpha, jph);
+                            dc[j].a1 = cend[j].a1 - c0[j].a1; dc[j].g = cend[j].g - c0[j].g;
+                            dc[j].lp = cend[j].lp - c0[j].lp; dc[j].amp0 = cend[j].amp0 - c0[j].amp0;
+                            dc[j].amp1 = cend[j].amp1 - c0[j].amp1; dc[j].br = cend[j].br - c0[j].br;
+                        }
+                        c_valid = true;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) {     // second half: start from the block's midpoint
+                            c0[j].a1 = fmaf(dc[j].a1, 0.5f, c0[j].a1); c0[j].g = fmaf(dc[j].g, 0.5f, c0[j].g);
+                            c0[j].lp = fmaf(dc[j].lp, 0.5f, c0[j].lp); c0[j].amp0 = fmaf(dc[j].amp0, 0.5f, c0[j].amp0);
+                            c0[j].amp1 = fmaf(dc[j].amp1, 0.5f, c0[j].amp1); c0[j].br = fmaf(dc[j].br, 0.5f, c0[j].br);
+                        }
                     }
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) {  // the clocks stay literal f32 chains  (:861, :291)
-                        time = __fadd_rn(time, ndt);
-                        jph = __fadd_rn(jph, jinc);
-                    }
-                    const float alpha = fminf(time * inv_bl, 1.0f);
+                    for (int k = 0; k < 8; ++k) {
+                        float d1, nz;
+                        noise(s8[k], d1, nz);
+                        const float t = (float)k * 0.0625f;
+                        float acc = 0.0f;
 #pragma unroll
-                    for (int j = 0; j < FPT; ++j) {
-                        c0[j] = cend[j];
-                        cend[j] = coeffs(L[j], alpha, jph);
-                        dc[j].a1 = cend[j].a1 - c0[j].a1; dc[j].g = cend[j].g - c0[j].g;
-                        dc[j].lp = cend[j].lp - c0[j].lp; dc[j].amp0 = cend[j].amp0 - c0[j].amp0;
-                        dc[j].amp1 = cend[j].amp1 - c0[j].amp1; dc[j].br = cend[j].br - c0[j].br;
+                        for (int j = 0; j < NJ; ++j) {
+                            Coef c;
+                            c.a1 = fmaf(dc[j].a1, t, c0[j].a1); c.g = fmaf(dc[j].g, t, c0[j].g);
+                            c.lp = fmaf(dc[j].lp, t, c0[j].lp); c.amp0 = fmaf(dc[j].amp0, t, c0[j].amp0);
+                            c.amp1 = fmaf(dc[j].amp1, t, c0[j].amp1); c.br = fmaf(dc[j].br, t, c0[j].br);
+                            acc += tick(L[j], c, s8[k], d1, nz);
+                        }
+                        v[k] = acc;
                     }
-                    c_valid = true;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < FPT; ++j) {     // second half: start from the block's midpoint
-                        c0[j].a1 = fmaf(dc[j].a1, 0.5f, c0[j].a1); c0[j].g = fmaf(dc[j].g, 0.5f, c0[j].g);
-                        c0[j].lp = fmaf(dc[j].lp, 0.5f, c0[j].lp); c0[j].amp0 = fmaf(dc[j].amp0, 0.5f, c0[j].amp0);
-                        c0[j].amp1 = fmaf(dc[j].amp1, 0.5f, c0[j].amp1); c0[j].br = fmaf(dc[j].br, 0.5f, c0[j].br);
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    float d1, nz;
-                    noise(s8[k], d1, nz);
-                    const float t = (float)k * 0.0625f;
-                    float acc = 0.0f;
-#pragma unroll
-                    for (int j = 0; j < FPT; ++j) {
-                        Coef c;
-                        c.a1 = fmaf(dc[j].a1, t, c0[j].a1); c.g = fmaf(dc[j].g, t, c0[j].g);
-                        c.lp = fmaf(dc[j].lp, t, c0[j].lp); c.amp0 = fmaf(dc[j].amp0, t, c0[j].amp0);
-                        c.amp1 = fmaf(dc[j].amp1, t, c0[j].amp1); c.br = fmaf(dc[j].br, t, c0[j].br);
-                        acc += tick(L[j], c, s8[k], d1, nz);
-                    }
-                    v[k] = acc;
-                }
+                };
+                if (FPT == 1 || r >= r_join) interp_block(std::integral_constant<int, FPT>{});
+                else interp_block(std::integral_constant<int, 1>{});
             } else if (!hand) {
                 // a kink somewhere in the warp: exact coefficients every sample, one inlined wrap test per sample
                 const float s8[8] = { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w };
