@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 #define GRAIL_NUM_FORMANTS 8 /* reference NUM_FORMANTS, src/lib.rs:24 */
-#define GRAIL_ABI_VERSION 1
+#define GRAIL_ABI_VERSION 2   /* 2: phoneme-level plans, grail_cuda_transcribe_batch */
 
 typedef enum grail_status {
     GRAIL_OK = 0,
