@@ -320,6 +320,13 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
         }
     }
     P.fflags[(U.f_off + ns + ((count - 1) & ~127u)) >> 7] = odd ? 1u : 0u;   // the last (possibly partial) 128-block
+    if (it.n0 + it.len == U.n_samples && off + count == it.len) {
+        // the lane that wrote the utterance's last sample rounds the row up: k_phase_pair copies F_t in groups of 8
+        // and the flag words in pairs, so nothing it touches is left unwritten (the values themselves are unused)
+        const uint32_t n = U.n_samples;
+        for (uint32_t i = n; i < ((n + 7u) & ~7u); ++i) P.F[U.f_off + i] = 0.0f;
+        if ((((n - 1u) >> 7) & 1u) == 0u) P.fflags[((U.f_off + n - 1u) >> 7) + 1u] = 0u;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

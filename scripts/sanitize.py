@@ -25,3 +25,13 @@ while True:
     if len(x) == 0: break
     n += len(x)
 print("stream", n)
+# phoneme-level input (k_select) and an interleaved group of 32 equally long utterances
+v = g.voices.generic()
+lists = [[0, 3, 4]] * 33 + [[3]]
+ids = np.concatenate([np.asarray(p, np.uint8) for p in lists])
+poffs = np.concatenate([[0], np.cumsum([len(p) for p in lists])]).astype(np.uint32)
+pvp = np.zeros(len(lists), g.VOICE_DT); pvp[:] = v.params(0); pvp["jitter_seed"] = np.arange(len(lists))
+ctx.set_option("pscan_min_samples", 1 << 18); ctx.set_option("pscan_cost_model", 1)
+ctx.set_option("min_chunk", 2048); ctx.set_option("target_lanes", 1 << 20)
+plan = ctx.plan_phonemes(ids, poffs, v.storage(), pvp, center_frequency=np.full(len(lists), v.center_frequency, np.float32))
+plan.launch(); o = plan.read_output(); print("phonemes", len(o), float(np.abs(o).sum())); plan.close()
