@@ -118,6 +118,24 @@ def measured_peaks() -> dict:
         return {}
 
 
+def bind_to_gpu_cpus(device_index: int):
+    """pin the calling process to the CPUs NVML reports as local to the GPU; returns the mask size or None"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def cpu_baseline_run(n_utts: int, threads: int, rank: int = 0):
     """the reference's CPU algorithm (oracle restatement, -O3 strict f32) over `threads` host threads"""
     from oracle import oracle as O
@@ -173,6 +191,11 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
+    # NUMA: keep this rank's threads (and therefore its pinned host buffers, which are placed where they are first
+    # touched) on the CPUs next to its GPU; with 8 ranks the 8 concurrent 0.9 GB device-to-host copies otherwise
+    # cross sockets.  The CPU baseline leg widens the mask again.
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_cpus(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -276,6 +299,7 @@ def run_ours(args):
                     "peak_source": "MEASURED_PEAKS.json (measured)" if peaks.get("hbm_gbs") else "absent"},
         }
         # ---------------- CPU baseline on this box's host cores (bounded sample) ----------------
+        os.sched_setaffinity(0, all_cpus)
         cores = host_cores()
         nb = max(cores, min(N_UTTS, 32 * cores))
         cpu_baseline_run(max(1, nb // 8), cores)
@@ -296,7 +320,8 @@ def run_ours(args):
                        "samples_per_step_per_gpu": n_samples, "l2": "inputs larger than L2 (2.7 GB touched per step)",
                        "parallelism": f"utterance-sharded x{world}, no data-path collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "api": "grail_cuda_synthesize_batch (host records in, pinned f32 out)"},
+                    "steps": e2e_steps, "api": "grail_cuda_synthesize_batch (host records in, pinned f32 out)",
+                    "cpus_bound_per_rank": numa},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "kernels_ms": kern, "rtf_per_gpu": value / world / SAMPLE_RATE, "checksum": checksum,
         }
