@@ -274,6 +274,15 @@ def run_ours(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * n_samples * e2e_steps / e2e_s
     checksum = float(np.abs(host_out[: 220476]).sum())
+    # the same call with i16 PCM out (what the reference's WAV path keeps, examples/cli.rs:49-51): half the D2H bytes
+    host_pcm = ctx.pinned_empty(n_samples, np.int16)
+    ctx.synthesize_batch(elems, offs, vp, out=host_pcm, out_offsets=oo, fmt=g.I16)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.synthesize_batch(elems, offs, vp, out=host_pcm, out_offsets=oo, fmt=g.I16)
+    barrier()
+    e2e_i16_value = world * n_samples * e2e_steps / max_over_ranks(time.perf_counter() - t0)
 
     line = None
     if rank == 0:
@@ -322,6 +331,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "api": "grail_cuda_synthesize_batch (host records in, pinned f32 out)",
                     "cpus_bound_per_rank": numa},
+            "e2e_i16": {"value": e2e_i16_value, "unit": UNIT, "d2h_bytes_per_step": int(n_samples * 2),
+                        "api": "grail_cuda_synthesize_batch_i16 (the reference's WAV sample format, pinned i16 out)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "kernels_ms": kern, "rtf_per_gpu": value / world / SAMPLE_RATE, "checksum": checksum,
         }

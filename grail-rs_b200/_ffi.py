@@ -47,7 +47,7 @@ EXPORTS = [
     "grail_cuda_abi_version", "grail_cuda_device_count", "grail_cuda_status_string", "grail_cuda_create",
     "grail_cuda_destroy", "grail_cuda_last_error", "grail_cuda_stream_handle", "grail_cuda_synchronize",
     "grail_cuda_set_option", "grail_cuda_host_alloc", "grail_cuda_host_free", "grail_cuda_count_samples",
-    "grail_cuda_transcribe_batch", "grail_cuda_synthesize_batch", "grail_cuda_plan_create", "grail_cuda_plan_create_phoneme_elems",
+    "grail_cuda_transcribe_batch", "grail_cuda_synthesize_batch", "grail_cuda_synthesize_batch_i16", "grail_cuda_plan_create", "grail_cuda_plan_create_phoneme_elems",
     "grail_cuda_plan_create_phonemes", "grail_cuda_plan_destroy",
     "grail_cuda_plan_join", "grail_cuda_plan_total_samples", "grail_cuda_plan_out_offsets", "grail_cuda_plan_launch", "grail_cuda_plan_launch_interleaved",
     "grail_cuda_plan_device_output", "grail_cuda_plan_read_output", "grail_cuda_plan_timings",
@@ -82,6 +82,7 @@ def lib() -> C.CDLL:
         "grail_cuda_count_samples": (i32, [vp, vp, vp, u32, vp]),
         "grail_cuda_transcribe_batch": (i32, [vp, vp, u32, vp, u32, i32, i32, vp, u64, vp, i32]),
         "grail_cuda_synthesize_batch": (i32, [vp, vp, vp, vp, u32, vp, vp, i32]),
+        "grail_cuda_synthesize_batch_i16": (i32, [vp, vp, vp, vp, u32, vp, vp, i32]),
         "grail_cuda_plan_create": (i32, [vp, vp, vp, vp, u32, C.POINTER(vp)]),
         "grail_cuda_plan_create_phoneme_elems": (i32, [vp, vp, vp, vp, u32, u32, vp, vp, u32, C.POINTER(vp)]),
         "grail_cuda_plan_create_phonemes": (i32, [vp, vp, vp, vp, vp, u32, u32, vp, vp, u32, C.POINTER(vp)]),

@@ -216,7 +216,8 @@ class Context:
 
     # -- one-shot (host buffers in, host buffer out): the drop-in for draining the iterator chain
     def synthesize_batch(self, elems: np.ndarray, utt_offsets: np.ndarray, voices: np.ndarray,
-                         out: Optional[np.ndarray] = None, out_offsets: Optional[np.ndarray] = None):
+                         out: Optional[np.ndarray] = None, out_offsets: Optional[np.ndarray] = None, fmt: int = _ffi.F32):
+        """drain a batch of chains into `out` (f32, or i16 as the reference's WAV writer converts: fmt=_ffi.I16)"""
         e = np.ascontiguousarray(elems, SEQ_ELEM_DT)
         offs = np.ascontiguousarray(utt_offsets, np.uint32)
         v = np.ascontiguousarray(voices, VOICE_DT).reshape(-1)
@@ -226,9 +227,13 @@ class Context:
         if out_offsets is None:
             out_offsets = np.concatenate([[0], np.cumsum(count_samples(e, offs, v))]).astype(np.uint64)
         oo = np.ascontiguousarray(out_offsets, np.uint64)
+        dt = np.float32 if fmt == _ffi.F32 else np.int16
         if out is None:
-            out = np.empty(int(oo[-1]), np.float32)
-        self._check(self._L.grail_cuda_synthesize_batch(self._h, ptr(e), ptr(offs), ptr(v), n, ptr(out), ptr(oo), 0))
+            out = np.empty(int(oo[-1]), dt)
+        if out.dtype != dt:
+            raise ValueError("output buffer dtype does not match the sample format")
+        fn = self._L.grail_cuda_synthesize_batch if fmt == _ffi.F32 else self._L.grail_cuda_synthesize_batch_i16
+        self._check(fn(self._h, ptr(e), ptr(offs), ptr(v), n, ptr(out), ptr(oo), 0))
         return out, oo
 
     def plan(self, elems: np.ndarray, utt_offsets: np.ndarray, voices: np.ndarray) -> "Plan":

@@ -156,6 +156,11 @@ int grail_cuda_transcribe_batch(const char* const* texts, const size_t* text_byt
 int grail_cuda_synthesize_batch(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_t* utt_offsets,
                                 const grail_voice_params* voices, uint32_t n_utts, float* out,
                                 const uint64_t* out_offsets, int out_is_device);
+/* the same with the samples converted on the device as the reference's WAV writer does, `(x * i16::MAX as f32) as i16`
+ * (examples/cli.rs:49-51: truncating, saturating, NaN -> 0): half the device-to-host bytes */
+int grail_cuda_synthesize_batch_i16(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_t* utt_offsets,
+                                    const grail_voice_params* voices, uint32_t n_utts, int16_t* out,
+                                    const uint64_t* out_offsets, int out_is_device);
 
 /* ---- resident plans (throughput path: inputs stay in HBM between launches) ------------------ */
 int  grail_cuda_plan_create(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_t* utt_offsets,

@@ -150,6 +150,11 @@ def test_i16_output(ctx, oracle):
     ref = np.trunc(want.astype(np.float32) * np.float32(32767.0)).astype(np.int16)   # examples/cli.rs:50
     assert len(pcm) == len(ref) and np.abs(pcm.astype(np.int32) - ref.astype(np.int32)).max() <= 4
     plan.close()
+    # the one-shot i16 entry point gives the very same PCM (pageable destination, non-zero first offset)
+    oo = np.array([3, 3 + len(ref)], np.uint64)
+    buf = np.full(len(ref) + 5, -7, np.int16)
+    got, _ = ctx.synthesize_batch(elems, offs, vp, out=buf, out_offsets=oo, fmt=g.I16)
+    assert np.array_equal(got[3:3 + len(ref)], pcm) and (got[:3] == -7).all() and (got[-2:] == -7).all()
 
 
 def test_count_mismatch_is_reported(ctx):
