@@ -106,6 +106,43 @@ __device__ __forceinline__ float frcp(float x)
     return r;
 }
 
+// Packed fp32 (sm_100: FFMA2 / FADD2 / FMUL2 on 64-bit register pairs): one issue slot for two IEEE operations, each
+// half rounded exactly like its scalar counterpart.  k_formant is issue-bound and a lane's two formants run the very
+// same instruction sequence on different data, so its inner loop carries them as (formant 0, formant 1) pairs.
+// A scalar that both halves share is written pk(s, s): ptxas folds it into the instruction's broadcast operand form.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pk(float lo, float hi)
+{
+    f2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk(f2_t x, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x)); }
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c)
+{
+    f2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f2_t add2(f2_t a, f2_t b)
+{
+    f2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2_t sub2(f2_t a, f2_t b)
+{
+    f2_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b)
+{
+    f2_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // largest index i in [0, n) with key(i) <= v; the caller guarantees key(0) <= v
 template <typename F>
 __device__ __forceinline__ uint32_t last_le(uint32_t n, F key, int64_t v)
@@ -1373,6 +1410,8 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
     Coef c0[FPT], dc[FPT];
 #pragma unroll
     for (int j = 0; j < FPT; ++j) { c0[j] = cend[j]; dc[j] = cend[j]; }
+    struct Coef2 { f2_t a1, g, lp, amp0, amp1, br; };
+    Coef2 p0 = { 0ull, 0ull, 0ull, 0ull, 0ull, 0ull }, pd = p0;   // packed block start / block delta (FPT = 2)
     bool hand = false, warp_exact = false;
     int half = 0;
     for (int r = -(int)wmax; r < (int)lmax; r += 8, half ^= 1) {
@@ -1443,7 +1482,64 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
                         v[k] = acc;
                     }
                 };
-                if (FPT == 1 || r >= r_join) interp_block(std::integral_constant<int, FPT>{});
+                // Both slots running (FPT = 2): the same block with the two formants carried as packed pairs.  Every
+                // packed operation rounds each half exactly as the scalar code above does (b' = 2 v1 - b is written
+                // (v1 + v1) - b: the doubling is exact), so the two forms give the same bits.
+                auto interp_block2 = [&]() {
+                    if (half == 0) {
+                        if (!c_valid) {
+                            const float alpha = fminf(time * inv_bl, 1.0f);
+#pragma unroll
+                            for (int j = 0; j < FPT; ++j) cend[j] = coeffs(L[j], alpha, jph);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {  // the clocks stay literal f32 chains  (:861, :291)
+                            time = __fadd_rn(time, ndt);
+                            jph = __fadd_rn(jph, jinc);
+                        }
+                        const float alpha = fminf(time * inv_bl, 1.0f);
+                        const Coef s0 = cend[0], s1 = cend[FPT - 1];
+#pragma unroll
+                        for (int j = 0; j < FPT; ++j) cend[j] = coeffs(L[j], alpha, jph);
+                        const Coef e0 = cend[0], e1 = cend[FPT - 1];
+                        p0.a1 = pk(s0.a1, s1.a1); p0.g = pk(s0.g, s1.g); p0.lp = pk(s0.lp, s1.lp);
+                        p0.amp0 = pk(s0.amp0, s1.amp0); p0.amp1 = pk(s0.amp1, s1.amp1); p0.br = pk(s0.br, s1.br);
+                        pd.a1 = sub2(pk(e0.a1, e1.a1), p0.a1); pd.g = sub2(pk(e0.g, e1.g), p0.g);
+                        pd.lp = sub2(pk(e0.lp, e1.lp), p0.lp); pd.amp0 = sub2(pk(e0.amp0, e1.amp0), p0.amp0);
+                        pd.amp1 = sub2(pk(e0.amp1, e1.amp1), p0.amp1); pd.br = sub2(pk(e0.br, e1.br), p0.br);
+                        c_valid = true;
+                    } else {
+                        const f2_t hf = pk(0.5f, 0.5f);                 // second half: start from the block's midpoint
+                        p0.a1 = fma2(pd.a1, hf, p0.a1); p0.g = fma2(pd.g, hf, p0.g); p0.lp = fma2(pd.lp, hf, p0.lp);
+                        p0.amp0 = fma2(pd.amp0, hf, p0.amp0); p0.amp1 = fma2(pd.amp1, hf, p0.amp1); p0.br = fma2(pd.br, hf, p0.br);
+                    }
+                    f2_t A = pk(L[0].a, L[FPT - 1].a), B = pk(L[0].b, L[FPT - 1].b), Cc = pk(L[0].c, L[FPT - 1].c);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        float d1, nz;
+                        noise(s8[k], d1, nz);
+                        const float tk = (float)k * 0.0625f;
+                        const f2_t t = pk(tk, tk), saw2 = pk(s8[k], s8[k]), d2 = pk(d1, d1), n2 = pk(nz, nz);
+                        const f2_t a1 = fma2(pd.a1, t, p0.a1), g = fma2(pd.g, t, p0.g), lp = fma2(pd.lp, t, p0.lp);
+                        const f2_t amp0 = fma2(pd.amp0, t, p0.amp0), amp1 = fma2(pd.amp1, t, p0.amp1), br = fma2(pd.br, t, p0.br);
+                        const f2_t nw = fma2(br, d2, saw2);                              // :531
+                        A = fma2(lp, sub2(nw, A), A);                                    // :538
+                        const f2_t v0 = mul2(A, fma2(amp1, n2, amp0));                   // :544-550
+                        const f2_t v3 = sub2(v0, Cc);                                    // :565
+                        const f2_t v1 = mul2(a1, fma2(g, v3, B));
+                        const f2_t v2 = fma2(g, v1, Cc);
+                        B = sub2(add2(v1, v1), B);
+                        Cc = sub2(add2(v2, v2), Cc);
+                        float x0, x1;
+                        unpk(v1, x0, x1);
+                        v[k] = (0.0f + x0) + x1;
+                    }
+                    unpk(A, L[0].a, L[FPT - 1].a);
+                    unpk(B, L[0].b, L[FPT - 1].b);
+                    unpk(Cc, L[0].c, L[FPT - 1].c);
+                };
+                if (FPT == 2 && r >= r_join) interp_block2();
+                else if (FPT == 1) interp_block(std::integral_constant<int, FPT>{});
                 else interp_block(std::integral_constant<int, 1>{});
             } else if (!hand) {
                 // a kink somewhere in the warp: exact coefficients every sample, one inlined wrap test per sample
