@@ -1482,9 +1482,8 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
                         v[k] = acc;
                     }
                 };
-                // Both slots running (FPT = 2): the same block with the two formants carried as packed pairs.  Every
-                // packed operation rounds each half exactly as the scalar code above does (b' = 2 v1 - b is written
-                // (v1 + v1) - b: the doubling is exact), so the two forms give the same bits.
+                // Both slots running (FPT = 2): the same block with the two formants carried as packed pairs (each half
+                // of a packed operation rounds exactly like its scalar counterpart).
                 auto interp_block2 = [&]() {
                     if (half == 0) {
                         if (!c_valid) {
@@ -1526,10 +1525,12 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
                         A = fma2(lp, sub2(nw, A), A);                                    // :538
                         const f2_t v0 = mul2(A, fma2(amp1, n2, amp0));                   // :544-550
                         const f2_t v3 = sub2(v0, Cc);                                    // :565
-                        const f2_t v1 = mul2(a1, fma2(g, v3, B));
-                        const f2_t v2 = fma2(g, v1, Cc);
+                        // v1 = a1 (g v3 + b) and c' = 2 (c + g v1) - c, regrouped so that the loop-carried chains are
+                        // b -> a1 b -> v1 -> 2 v1 - b (4 operations) and c -> v3 -> v1 -> c' (3) instead of 6: the
+                        // same operation count, half the dependent latency per sample
+                        const f2_t v1 = fma2(mul2(a1, g), v3, mul2(a1, B));
+                        Cc = fma2(add2(g, g), v1, Cc);
                         B = sub2(add2(v1, v1), B);
-                        Cc = sub2(add2(v2, v2), Cc);
                         float x0, x1;
                         unpk(v1, x0, x1);
                         v[k] = (0.0f + x0) + x1;
