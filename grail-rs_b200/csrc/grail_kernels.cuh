@@ -1533,7 +1533,7 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
                         B = sub2(add2(v1, v1), B);
                         float x0, x1;
                         unpk(v1, x0, x1);
-                        v[k] = (0.0f + x0) + x1;
+                        v[k] = x0 + x1;
                     }
                     unpk(A, L[0].a, L[FPT - 1].a);
                     unpk(B, L[0].b, L[FPT - 1].b);
