@@ -843,7 +843,9 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
         pl->last_launches++;
     }
     if (pl->n_items) {
-        k_phase_pair<<<(pl->n_utts + PH_UTTS - 1) / PH_UTTS, PH_UTTS * 64, 0, s>>>(P);
+        const uint32_t ctas = (pl->n_utts + PH_UTTS - 1) / PH_UTTS;
+        if (ctas > 2u * (uint32_t)ctx->prop.multiProcessorCount) k_phase_pair<true><<<ctas, PH_UTTS * 64, 0, s>>>(P);
+        else k_phase_pair<false><<<ctas, PH_UTTS * 64, 0, s>>>(P);
         pl->last_launches++;
     }
     CU(ctx, cudaEventRecord(ev[3], s));
