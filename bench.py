@@ -41,7 +41,7 @@ FLOPS_PER_SAMPLE = 762
 FLOPS_PER_SAMPLE_FORMANT = 736
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_formant launch on this workload, from the committed
 # `ncu --set full` capture (profiles/r1_k_formant_ncu_full.txt: 1.567 GB read + 0.868 GB written; algorithmic 1.806 GB)
-NCU_TRAFFIC_BYTES = 1373341000 + 861585152
+NCU_TRAFFIC_BYTES = 1373045000 + 862064384
 
 
 def host_cores() -> int:
@@ -300,8 +300,9 @@ def run_ours(args):
             "note": "achieved counts the reference's as-written flops (SURVEY 8d); the kernel executes fewer: 4 of the "
                     "8 formants of the default voice are exactly zero and are skipped, and the 6 per-sample filter "
                     "coefficients are interpolated between exact 16-sample end points, so frac exceeds 1; the honest "
-                    "efficiency figure is ncu's (profiles/r1_k_formant_ncu_full.txt): 1.18e9 warp instructions per "
-                    "launch, 63 % of the issue slots busy",
+                    "efficiency figures are ncu's (profiles/r1_k_formant_ncu_full.txt): 9.1e8 warp instructions per "
+                    "launch, more than half of them packed FFMA2/FADD2/FMUL2 that hold the FP32 pipe for two cycles, "
+                    "issue slots 55 % busy, FMA-heavy pipe 46 % busy",
             "mufu_peak_per_s": probe["mufu_ops"],
             "hbm": {"achieved": hbm_bytes / (formant_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                     "frac": (hbm_bytes / (formant_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
