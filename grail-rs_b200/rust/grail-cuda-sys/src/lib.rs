@@ -36,6 +36,38 @@ impl Ctx {
     }
 }
 
+impl Ctx {
+    /// `synthesize_batch` with the samples converted on the device as the reference's WAV writer does
+    /// (`(x * i16::MAX as f32) as i16`, examples/cli.rs:49-51): half the device-to-host bytes.
+    pub fn synthesize_batch_i16(&mut self, elems: &[grail_seq_elem], utt_offsets: &[u32], voices: &[grail_voice_params],
+                                out: &mut [i16], out_offsets: &[u64]) -> Result<(), i32> {
+        let rc = unsafe {
+            grail_cuda_synthesize_batch_i16(self.0, elems.as_ptr(), utt_offsets.as_ptr(), voices.as_ptr(), voices.len() as u32,
+                                            out.as_mut_ptr(), out_offsets.as_ptr(), 0)
+        };
+        if rc == 0 { Ok(()) } else { Err(rc) }
+    }
+}
+
+/// The reference's `Transcriber` (src/lib.rs:1098-1207) over a batch of texts on all host cores (host only).
+/// `rules` must be sorted by string; returns (phoneme ids, utterance offsets) in the layout `Plan::from_phonemes` takes.
+pub fn transcribe_batch(texts: &[&str], rules: &[(&std::ffi::CStr, &[u8])], case_sensitive: bool, leading_silence: bool)
+                        -> Result<(Vec<u8>, Vec<u32>), i32> {
+    let ptrs: Vec<*const std::os::raw::c_char> = texts.iter().map(|t| t.as_ptr() as *const _).collect();
+    let lens: Vec<usize> = texts.iter().map(|t| t.len()).collect();
+    let crules: Vec<grail_transcription_rule> = rules.iter()
+        .map(|(s, p)| grail_transcription_rule { string: s.as_ptr(), phonemes: p.as_ptr(), n_phonemes: p.len() as u32 })
+        .collect();
+    let mut offs = vec![0u32; texts.len() + 1];
+    let count = |ids: *mut u8, cap: u64, offs: &mut Vec<u32>| unsafe {
+        grail_cuda_transcribe_batch(ptrs.as_ptr(), lens.as_ptr(), texts.len() as u32, crules.as_ptr(), crules.len() as u32,
+                                    case_sensitive as i32, leading_silence as i32, ids, cap, offs.as_mut_ptr(), 0)
+    };
+    match count(std::ptr::null_mut(), 0, &mut offs) { 0 => {}, e => return Err(e) }
+    let mut ids = vec![0u8; *offs.last().unwrap() as usize];
+    match count(ids.as_mut_ptr(), ids.len() as u64, &mut offs) { 0 => Ok((ids, offs)), e => Err(e) }
+}
+
 /// A batch resident in HBM (`grail_plan`): built once, launched many times.
 pub struct Plan(*mut grail_plan);
 
