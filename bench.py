@@ -39,6 +39,9 @@ N_PHONEMES = 10
 # dominant kernel (k_formant) covers = everything but the scalar frequency/phase lane (26 flops)
 FLOPS_PER_SAMPLE = 762
 FLOPS_PER_SAMPLE_FORMANT = 736
+# the same count when the formants whose amplitude is zero in every phoneme are left out, as the reference's result
+# allows (about 400 for the default voice's 4 active formants, minus the 26 of the frequency lane)
+FLOPS_PER_SAMPLE_FORMANT_ACTIVE = 374
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_formant launch on this workload, from the committed
 # `ncu --set full` capture (profiles/r1_k_formant_ncu_full.txt: 1.567 GB read + 0.868 GB written; algorithmic 1.806 GB)
 NCU_TRAFFIC_BYTES = 1373045000 + 862064384
@@ -297,6 +300,7 @@ def run_ours(args):
             "frac": achieved_tf / peak_tf, "traffic": NCU_TRAFFIC_BYTES,
             "peak_source": "FFMA issue-rate probe measured live in this run (MEASURED_PEAKS.json has no fp32 figure)",
             "flops_per_sample": FLOPS_PER_SAMPLE_FORMANT, "launch_ms": formant_ms,
+            "frac_active_formants": FLOPS_PER_SAMPLE_FORMANT_ACTIVE * n_samples / (formant_ms * 1e-3) / 1e12 / peak_tf,
             "note": "achieved counts the reference's as-written flops (SURVEY 8d); the kernel executes fewer: 4 of the "
                     "8 formants of the default voice are exactly zero and are skipped, and the 6 per-sample filter "
                     "coefficients are interpolated between exact 16-sample end points, so frac exceeds 1; the honest "
