@@ -54,7 +54,7 @@ EXPORTS = [
     "grail_cuda_plan_read_intermediates", "grail_cuda_plan_phase_scan_stats", "grail_cuda_stream_new", "grail_cuda_stream_push",
     "grail_cuda_stream_finish", "grail_cuda_stream_pull", "grail_cuda_stream_free", "grail_cuda_probe_fp32_peak",
     "grail_cuda_debug_clock_desc", "grail_cuda_debug_clock_asc", "grail_cuda_debug_lcg_jump",
-    "grail_cuda_debug_jitter_index",
+    "grail_cuda_debug_jitter_index", "grail_cuda_debug_div_check",
 ]
 
 
@@ -107,6 +107,7 @@ def lib() -> C.CDLL:
         "grail_cuda_debug_clock_asc": (None, [C.c_float, C.c_float, u64, C.POINTER(C.c_float), C.POINTER(u64), C.POINTER(i32)]),
         "grail_cuda_debug_lcg_jump": (u32, [u32, u64]),
         "grail_cuda_debug_jitter_index": (u64, [i32, i32, i32, u64]),
+        "grail_cuda_debug_div_check": (i32, [vp, u32, u64, C.POINTER(u64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

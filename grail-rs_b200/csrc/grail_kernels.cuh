@@ -366,6 +366,25 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
     }
 }
 
+// test hook: div_by_const against the IEEE division on pseudo-random pairs (a spread over ~60 binades around the
+// Sequencer's operating range, b over the blend lengths the guard admits); counts the pairs that differ in any bit
+__global__ void k_debug_div_check(uint32_t seed, uint32_t per_thread, unsigned long long* mismatches)
+{
+    uint32_t s = seed ^ ((blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u);
+    unsigned long long bad = 0;
+    for (uint32_t i = 0; i < per_thread; ++i) {
+        s = lcg_step(s); const uint32_t ma = s;
+        s = lcg_step(s); const uint32_t mb = s;
+        s = lcg_step(s); const uint32_t ex = s;
+        // mantissas from the draws, exponents: a in 2^[-40, 20), b in 2^[-30, 30)
+        const float a = __uint_as_float((ma >> 9) | ((127u - 40u + (ex >> 8) % 60u) << 23));
+        const float b = __uint_as_float((mb >> 9) | ((127u - 30u + (ex >> 20) % 60u) << 23));
+        const float y = div_const_rcp(b);
+        bad += __float_as_uint(div_by_const(a, b, y)) != __float_as_uint(sdiv(a, b));
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K2 (serial-chain form): bit-exact carrier phase and polyBLEP saw.  The f32 chain
 // phase <- RN(phase + F_t) is the only truly serial dependency of the path; blocks of 8 are run

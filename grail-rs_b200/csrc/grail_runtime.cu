@@ -1513,6 +1513,24 @@ void grail_cuda_debug_clock_asc(float x, float d, uint64_t max_steps, float* x_o
     *x_out = r.x; *steps = r.steps; *stuck = r.stuck;
 }
 uint32_t grail_cuda_debug_lcg_jump(uint32_t seed, uint64_t n) { return lcg_jump(seed, n); }
+int grail_cuda_debug_div_check(grail_ctx* ctx, uint32_t seed, uint64_t n_pairs, uint64_t* mismatches)
+{
+    if (!ctx || !mismatches) return GRAIL_ERR_INVALID_ARG;
+    CU(ctx, cudaSetDevice(ctx->device));
+    unsigned long long* d = nullptr;
+    CU(ctx, cudaMalloc(&d, 8));
+    CU(ctx, cudaMemsetAsync(d, 0, 8, ctx->stream));
+    const uint32_t per_thread = 1024, threads = 256;
+    const uint64_t blocks = (n_pairs + (uint64_t)per_thread * threads - 1) / ((uint64_t)per_thread * threads);
+    k_debug_div_check<<<(unsigned)std::min<uint64_t>(blocks, 1u << 20), threads, 0, ctx->stream>>>(seed, per_thread, d);
+    unsigned long long h = 0;
+    cudaError_t e = cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return set_err(ctx, GRAIL_ERR_CUDA, "div check: %s", cudaGetErrorString(e));
+    *mismatches = h;
+    return GRAIL_OK;
+}
 uint64_t grail_cuda_debug_jitter_index(int gen, int which /*0 cur, 1 next*/, int i, uint64_t w)
 {
     if (gen < 0) return which ? jit_freq_next_idx(w) : jit_freq_cur_idx(w);

@@ -326,3 +326,12 @@ def test_synthesize_resampled_property(ctx, oracle):
         e = np.array([spec[(freqs >= lo) & (freqs < hi)].sum() for lo, hi in zip(edges[:-1], edges[1:])])
         return np.log10(e / e.sum())
     assert np.abs(bands(a, 44100.0) - bands(b, 22050.0)).max() < 1.0      # within a decade in every band
+
+
+def test_division_by_segment_constant_is_ieee_exact(ctx):
+    """k_frequency divides the Sequencer clock by the segment's blend length through RN(1/b) and one FMA correction
+    (Markstein): 2^31 pseudo-random pairs across 60 binades each must equal the IEEE quotient bit for bit"""
+    import ctypes as C
+    bad = C.c_uint64(123)
+    rc = ctx._L.grail_cuda_debug_div_check(ctx._h, 20261017, 1 << 31, C.byref(bad))
+    assert rc == 0 and bad.value == 0, (rc, bad.value)
