@@ -518,13 +518,10 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
     if (target == 0) {
         int occ = formant_occupancy_of((int)nw, (int)pl->fpt);
         if (occ < 1) occ = 1;
-        if (pl->pipelined) {
-            // leave room on every SM for the next launch's phase kernel (2 warps per utterance, all utterances
-            // resident at once: ~32K registers) so that it really runs under this launch's formant kernel
-            const int cta_regs = std::max(1, 65536 / occ);
-            const int reserve = (32768 + cta_regs - 1) / cta_regs;
-            occ = std::max(occ - reserve, (occ + 1) / 2);
-        } else {
+        {
+            // (pipelined plans use the same target: the next launch's phase kernel needs two CTAs of 25 K registers per
+            // SM at most and finds them once the first formant CTAs retire; reserving room for it up front was
+            // measured slower -- 3.22 ms per step against 2.95 at the full target, 3.03 without pipelining)
             // Fewer, longer chunks beat full occupancy (the warm-up is paid per chunk): aim at 12 warps per SM with two
             // formants per lane (what 167 registers allow; measured at config 2: 6 CTAs/SM 1.69 ms, 5 -> 1.91, 4 -> 1.78)
             // and 3/4 of the resident warps with one, and keep the warps per SM a multiple of 4 so the four

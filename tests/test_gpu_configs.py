@@ -102,3 +102,31 @@ def test_parallel_phase_scan_matches_chain(ctx, oracle):
     finally:
         ctx.set_option("pscan_min_samples", 1 << 18)
         ctx.set_option("pscan_cost_model", 1)
+
+
+def test_pipelined_launches_match_in_order_launches(ctx):
+    """option "pipeline": consecutive launches of a plan overlap (the next launch's frequency / phase kernels run on a
+    second stream and scratch set under the current formant kernel).  Same bits as launching in order, whether the
+    launches share one output buffer or alternate between two."""
+    import torch
+    elems, offs, vp = W.config2(96, 4)
+    plan = ctx.plan(elems, offs, vp)
+    plan.launch()
+    want = plan.read_output().copy()
+    plan.close()
+    ctx.set_option("pipeline", 1)
+    try:
+        plan = ctx.plan(elems, offs, vp)
+        a = torch.zeros(plan.total_samples, dtype=torch.float32, device="cuda")
+        b = torch.zeros_like(a)
+        for i in range(5):
+            plan.launch(a.data_ptr() if i % 2 == 0 else b.data_ptr())
+        plan.join()
+        ctx.synchronize()
+        assert np.array_equal(a.cpu().numpy().view(np.uint32), want.view(np.uint32))
+        assert np.array_equal(b.cpu().numpy().view(np.uint32), want.view(np.uint32))
+        t = plan.timings()
+        assert t["n_launches"] == 3
+        plan.close()
+    finally:
+        ctx.set_option("pipeline", 0)
