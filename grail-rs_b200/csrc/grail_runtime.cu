@@ -44,6 +44,7 @@ struct grail_ctx {
     uint32_t max_chunk = 1u << 22;
     int      debug_taps = 0;
     uint32_t pscan_min = 1u << 18;   // utterances at least this long may get the exact parallel phase scan
+    int phase_lean = -1;             // k_phase_pair build: -1 by batch size, 0 latency build, 1 few-register build
     int interleave = 1;              // interleave equally long utterances chunk by chunk in k_formant's CTAs
     int pscan_cost_model = 1;        // 0: scan every utterance >= pscan_min (at most 16), whatever it costs
     int      zero_copy_out = 0;      // 1: k_formant stores straight into pinned host output (measured slower: 23 vs 50 GB/s over PCIe)
@@ -841,7 +842,8 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
     }
     if (pl->n_items) {
         const uint32_t ctas = (pl->n_utts + PH_UTTS - 1) / PH_UTTS;
-        if (ctas > 2u * (uint32_t)ctx->prop.multiProcessorCount) k_phase_pair<true><<<ctas, PH_UTTS * 64, 0, s>>>(P);
+        const bool lean = ctx->phase_lean < 0 ? ctas > 2u * (uint32_t)ctx->prop.multiProcessorCount : ctx->phase_lean != 0;
+        if (lean) k_phase_pair<true><<<ctas, PH_UTTS * 64, 0, s>>>(P);
         else k_phase_pair<false><<<ctas, PH_UTTS * 64, 0, s>>>(P);
         pl->last_launches++;
     }
@@ -993,6 +995,8 @@ int grail_cuda_set_option(grail_ctx* ctx, const char* key, double value)
         ctx->formants_per_lane = (int)value;
     } else if (!strcmp(key, "pipeline")) {
         ctx->pipeline = value != 0.0;
+    } else if (!strcmp(key, "phase_lean")) {
+        ctx->phase_lean = value < 0.0 ? -1 : (value != 0.0);
     } else if (!strcmp(key, "interleave")) {
         ctx->interleave = value != 0.0;
     } else if (!strcmp(key, "pscan_cost_model")) {

@@ -114,7 +114,8 @@ int  grail_cuda_synchronize(grail_ctx* ctx);
 /* tuning knobs: "warmup_nepers" (float, filter warm-up depth, default 13.8 ~ 1e-6),
  * "target_lanes" (int, time-chunks the planner aims for), "max_chunk" / "min_chunk" (samples),
  * "formants_per_lane" (1|2), "pipeline" (0|1: overlap consecutive launches of a plan), "pscan_min_samples",
- * "pscan_cost_model" (0|1), "zero_copy_out" (0|1) */
+ * "pscan_cost_model" (0|1), "zero_copy_out" (0|1), "interleave" (0|1: interleave equally long utterances chunk by
+ * chunk in the formant kernel's CTAs), "phase_lean" (-1 auto | 0 | 1: which build of the phase kernel) */
 int  grail_cuda_set_option(grail_ctx* ctx, const char* key, double value);
 
 /* pinned host memory for full-rate H2D/D2H (optional; pageable buffers also work) */
