@@ -66,3 +66,18 @@ def test_product_never_touches_the_oracle():
                             continue
                         bad.append(os.path.join(dp, fn))
     assert not bad, bad
+
+
+def test_public_headers_are_plain_c():
+    """include/*.h is what a cgo / bindgen / ctypes consumer reads: it must compile as C99, with no C++ or CUDA types"""
+    import subprocess, tempfile
+    inc = os.path.join(ROOT, "include")
+    src = ('#include "grail_cuda.h"\n#include "grail_cuda_debug.h"\n'
+           "int main(void) { grail_seq_elem e; grail_phoneme_elem p; grail_transcription_rule r; grail_voice_params v;\n"
+           "  (void)e; (void)p; (void)r; (void)v; return sizeof(grail_seq_elem) == 208 && sizeof(grail_phoneme_elem) == 16 ? 0 : 1; }\n")
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "hdr.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "hdr")
+        subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I" + inc, c, "-o", exe])
+        assert subprocess.call([exe]) == 0
