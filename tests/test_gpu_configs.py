@@ -130,3 +130,35 @@ def test_pipelined_launches_match_in_order_launches(ctx):
         plan.close()
     finally:
         ctx.set_option("pipeline", 0)
+
+
+def test_interleaved_planner_against_plain_order(ctx, oracle):
+    """100 utterances of three lengths in random order: groups of 32 equally long ones are interleaved chunk by chunk
+    (with empty padding items between groups), the rest stay consecutive.  Every utterance must come out where
+    out_offsets says, equal to the plain-order plan at rounding level and to the oracle within the tolerance."""
+    rng = np.random.default_rng(11)
+    v = g.voices.generic()
+    lists = [[0] + [int(x) for x in rng.integers(3, 5, int(n))] for n in rng.integers(1, 4, 100)]
+    elems, offs, vp = W.from_phonemes(lists, v, list(range(100)))
+    outs = {}
+    for inter in (1, 0):
+        ctx.set_option("interleave", inter)
+        ctx.set_option("min_chunk", 4096)
+        ctx.set_option("target_lanes", 100000)          # several chunks per utterance
+        try:
+            plan = ctx.plan(elems, offs, vp)
+            plan.launch()
+            outs[inter] = (plan.read_output().copy(), plan.out_offsets.copy())
+            plan.close()
+        finally:
+            ctx.set_option("interleave", 1)
+            ctx.set_option("min_chunk", 2048)
+            ctx.set_option("target_lanes", 0)
+    a, oo = outs[1]
+    b, oo_b = outs[0]
+    assert np.array_equal(oo, oo_b)
+    assert float(np.abs(a - b).max()) < 2e-6
+    for u in rng.choice(100, 10, replace=False):
+        want, _, _ = oracle.synthesize(elems[offs[u]:offs[u + 1]], vp[u])
+        st = W.parity_stats(a[oo[u]:oo[u + 1]], want)
+        assert st["max_abs"] <= MAX_ABS and st["snr_db"] >= MIN_SNR_DB, (u, st)
