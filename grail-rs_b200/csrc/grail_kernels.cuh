@@ -734,8 +734,11 @@ struct PScanDev {
     unsigned long long* inc;        // n rounded increments
     unsigned long long* bsum;       // scan spine
     unsigned char* cls;             // per step, from the current estimate: grid exponent g (bits 0-4), wraps (bit 5)
-    unsigned char* sflag;           // per step: bit0 parity of the carry into the high part, bit1 tie on a wrap step, bit2 parity of c at the tie
-    unsigned char* bpar;            // per 256-step block: parity transducer (bit1 has_tie, bit0 xor), then incoming parity
+    unsigned char* sflag;           // per step: bit0 parity of the carry into the high part, bit1 tie on a wrap step, bit2 parity of c at the tie, bit3 the tie is currently rounded up
+    unsigned char* bpar;            // per 256-step block: parity transducer (bit1 has_tie, bit0 xor)
+    unsigned char* bpin;            // per block: parity entering it (k_ps_parity_spine)
+    uint32_t* stamp;                // per block: the last round whose replay must redo it (its step classes changed)
+    uint32_t* lbk;                  // per block: first block of its look-back range when it was last replayed
     uint32_t* status;               // {mismatches, done, rounds, unsupported}
     uint32_t n;
     unsigned long long p0;          // phase at sample 0
@@ -820,7 +823,7 @@ __global__ void __launch_bounds__(1024) k_ps_scan_spine(PScanDev S, uint32_t nb)
 // Third scan pass, fused with what every step needs from the new estimate: (a) the proof -- the step redone with
 // real f32 operations must land on the next phase (counted into status[0] when `verify`), and (b) the step's class
 // for the next round's replay: rounding grid and "reaches 1.0".
-__global__ void __launch_bounds__(SCAN_THREADS) k_ps_scan_apply(PScanDev S, int verify)
+__global__ void __launch_bounds__(SCAN_THREADS) k_ps_scan_apply(PScanDev S, int verify, uint32_t next_round)
 {
     if (S.status[1] | S.status[3]) return;
     __shared__ unsigned long long sh[SCAN_THREADS / 32];
@@ -866,11 +869,19 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_ps_scan_apply(PScanDev S, int 
         }
     }
     static_assert(SCAN_ITEMS == 8, "class bytes are packed into one 8-byte store");
+    // a block whose classes changed (all of them after round 0) is stamped for the next round's replay; the others
+    // keep their increments, which depend on nothing else (k_ps_replay checks the stamps of its look-back range too)
     if (base + SCAN_ITEMS <= S.n) {
-        *reinterpret_cast<unsigned long long*>(S.cls + base) = cpack;
+        unsigned long long* cp = reinterpret_cast<unsigned long long*>(S.cls + base);
+        if (!verify || *cp != cpack) S.stamp[base / PS_BLOCK] = next_round;
+        *cp = cpack;
     } else {
         for (int i = 0; i < SCAN_ITEMS; ++i)
-            if (base + i < S.n) S.cls[base + i] = (unsigned char)(cpack >> (8 * i));
+            if (base + i < S.n) {
+                const unsigned char c = (unsigned char)(cpack >> (8 * i));
+                if (!verify || S.cls[base + i] != c) S.stamp[(base + i) / PS_BLOCK] = next_round;
+                S.cls[base + i] = c;
+            }
     }
     if (verify) {
         const unsigned m = __reduce_add_sync(0xffffffffu, bad);
@@ -884,7 +895,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_ps_scan_apply(PScanDev S, int 
 // parity flags.  Grids and wraps come from k_ps_classify.
 constexpr uint32_t PS_MAX_LOOKBACK = 1u << 16;
 
-__global__ void __launch_bounds__(128) k_ps_replay(PScanDev S)
+__global__ void __launch_bounds__(128) k_ps_replay(PScanDev S, uint32_t round)
 {
     if (S.status[1] | S.status[3]) return;                       // uniform over the grid
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -892,10 +903,19 @@ __global__ void __launch_bounds__(128) k_ps_replay(PScanDev S)
     const bool live = t0_ < S.n;                                 // dead lanes stay with the warp: no divergent exits
     const uint32_t t0 = live ? (uint32_t)t0_ : 0u;
     const uint32_t t1 = live ? (uint32_t)min((uint64_t)S.n, t0_ + PS_BLOCK) : 0u;
+    // Nothing this lane reads has changed since it last ran (the classes of its block and of its look-back range, whose
+    // first block it noted then): its increments, flags and block parity map stand.  After the second round this is
+    // true of almost every block.  (A range that changed in an earlier round was redone, and re-noted, in that round.)
+    bool todo = false;
+    if (live) {
+        if (round == 1u) todo = true;
+        else for (uint32_t bb = S.lbk[b]; bb <= b; ++bb) todo |= S.stamp[bb] == round;
+    }
+    if (!__any_sync(0xffffffffu, todo)) return;
     // Look back for the segment start, 4 class bytes at a time (t0 is a multiple of 256, so s0 stays 4-aligned).
     uint32_t s0 = t0, back = 0;
     uint32_t w4 = 0;
-    while (s0 >= 4 && back <= PS_MAX_LOOKBACK) {
+    while (todo && s0 >= 4 && back <= PS_MAX_LOOKBACK) {
         w4 = __ldg(reinterpret_cast<const uint32_t*>(S.cls + s0 - 4)) & 0x20202020u;
         if (w4) break;
         s0 -= 4;
@@ -904,6 +924,7 @@ __global__ void __launch_bounds__(128) k_ps_replay(PScanDev S)
     __syncwarp();
     if (back > PS_MAX_LOOKBACK) atomicOr(S.status + 3, 1u);      // a carrier slower than 0.7 Hz: serial chain instead
     if (w4) s0 = s0 - 4 + ((31 - __clz(w4)) >> 3) + 1;           // first step after the last wrap
+    if (todo) S.lbk[b] = (s0 ? s0 - 1u : 0u) / PS_BLOCK;          // the wrap step that ends the look-back is part of what was read
     unsigned long long L = (s0 == 0) ? (S.p0 & 0x1FFFFull) : 0ull;
     // one step: the low bits decide the rounding.  Only an exact tie on a wrap step (g == 17, low 17 bits == 2^16)
     // needs a bit from above them: the parity of the high part.  Those steps are rounded DOWN here and flagged;
@@ -920,7 +941,7 @@ __global__ void __launch_bounds__(128) k_ps_replay(PScanDev S)
     };
     unsigned long long inc;
     unsigned flag;
-    for (uint32_t s = s0; s < t0; ++s) step(__ldg(S.F + s), __ldg(S.cls + s), inc, flag);
+    for (uint32_t s = s0; todo && s < t0; ++s) step(__ldg(S.F + s), __ldg(S.cls + s), inc, flag);
     __syncwarp();
     // Parity of the high part Q = floor(P / 2^17): a non-tie step adds a known carry (bit 0 of its flag); a tie step
     // rounds to even, so Q is even after it whatever came before.  Per block the parity map is either p -> p ^ x or
@@ -929,7 +950,7 @@ __global__ void __launch_bounds__(128) k_ps_replay(PScanDev S)
     auto parity = [&](unsigned fl) { if (fl & 2u) { has_tie = 1; px = 0; } else px ^= fl & 1u; };
     // own block, four steps at a time: 16 bytes of F and 4 class bytes in, one full 32-byte sector of increments
     // and 4 flag bytes out
-    uint32_t s = t0;
+    uint32_t s = todo ? t0 : t1;
     for (; s + 4 <= t1; s += 4) {
         const float4 f4 = __ldg(reinterpret_cast<const float4*>(S.F + s));
         const uint32_t c4 = __ldg(reinterpret_cast<const uint32_t*>(S.cls + s));
@@ -951,14 +972,15 @@ __global__ void __launch_bounds__(128) k_ps_replay(PScanDev S)
         S.sflag[s] = (unsigned char)flag;
         parity(flag);
     }
-    if (live) S.bpar[b] = (unsigned char)((has_tie << 1) | px);
-    if (__any_sync(0xffffffffu, has_tie != 0) && (threadIdx.x & 31) == 0) atomicOr(S.status + 15, 1u);   // ties exist this round
+    if (todo) S.bpar[b] = (unsigned char)((has_tie << 1) | px);
+    if (has_tie) atomicMax(S.status + 15, b + 1u);   // 1 + the last block that holds a tie (0: none so far; sticky)
 }
 
 // exclusive scan of the block transducers -> incoming parity of every block (one CTA walks the spine)
 __global__ void __launch_bounds__(1024) k_ps_parity_spine(PScanDev S, uint32_t nblk)
 {
-    if (S.status[1] | S.status[3] | (S.status[15] ^ 1u)) return;     // no tie anywhere this round: nothing to fix
+    if (S.status[1] | S.status[3] | (S.status[15] == 0u)) return;    // no tie anywhere so far: nothing to fix
+    nblk = min(nblk, S.status[15]);                                  // parities past the last tie block are never read
     __shared__ unsigned sh[32];
     __shared__ unsigned carry;                       // parity entering the current stripe
     if (threadIdx.x == 0) carry = (unsigned)((S.p0 >> 17) & 1ull);
@@ -996,7 +1018,7 @@ __global__ void __launch_bounds__(1024) k_ps_parity_spine(PScanDev S, uint32_t n
         const unsigned pin = (excl & 2u) ? (excl & 1u) : ((carry ^ excl) & 1u);
         const unsigned pout = (incl & 2u) ? (incl & 1u) : ((carry ^ incl) & 1u);
         __syncthreads();
-        if (i < nblk) S.bpar[i] = (unsigned char)pin;
+        if (i < nblk) S.bpin[i] = (unsigned char)pin;
         if (threadIdx.x == 1023) carry = pout;
         __syncthreads();
     }
@@ -1004,16 +1026,23 @@ __global__ void __launch_bounds__(1024) k_ps_parity_spine(PScanDev S, uint32_t n
 // second walk with the incoming parity known: round every flagged tie to even
 __global__ void __launch_bounds__(128) k_ps_parity_fix(PScanDev S)
 {
-    if (S.status[1] | S.status[3] | (S.status[15] ^ 1u)) return;
+    if (S.status[1] | S.status[3]) return;
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t t0 = (uint64_t)b * PS_BLOCK;
-    if (t0 >= S.n) return;
+    if (t0 >= S.n || b >= S.status[15] || !(S.bpar[b] & 2u)) return;   // only blocks that hold a tie have anything to fix
     const uint32_t t1 = (uint32_t)min((uint64_t)S.n, t0 + PS_BLOCK);
-    unsigned p = S.bpar[b] & 1u;
+    unsigned p = S.bpin[b] & 1u;
     for (uint32_t t = (uint32_t)t0; t < t1; ++t) {
         const unsigned f = S.sflag[t];
         if (f & 2u) {
-            if (((p ^ (f >> 2)) & 1u) != 0u) S.inc[t] += 0x20000ull;   // (Q + c) odd: round half UP to the even multiple
+            // (Q + c) odd: round half UP to the even multiple.  Bit 3 remembers that this tie is currently rounded up:
+            // blocks the replay skipped this round still carry last round's decision, which the new incoming parity
+            // may confirm or reverse.
+            const unsigned want = (p ^ (f >> 2)) & 1u, have = (f >> 3) & 1u;
+            if (want != have) {
+                S.inc[t] += want ? 0x20000ull : ~0x20000ull + 1ull;
+                S.sflag[t] = (unsigned char)(f ^ 8u);
+            }
             p = 0;
         } else {
             p ^= f & 1u;
@@ -1029,7 +1058,6 @@ __global__ void k_ps_check(PScanDev S)
     S.status[2] += 1;
     if (S.status[0] == 0) S.status[1] = 1;      // converged: exact
     S.status[0] = 0;
-    S.status[15] = 0;
 }
 
 // phases -> polyBLEP saw in the tiled layout k_formant reads (same arithmetic as k_phase_pair's saw warp)

@@ -669,15 +669,19 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
         void *p = nullptr, *q = nullptr, *b = nullptr;
         int rc1 = pool_alloc(ctx, (n + 1) * 8, &p);
         if (!rc1) { pl->pscan_bufs.push_back(p); rc1 = pool_alloc(ctx, n * 8 + 8, &q); }
-        void *fl = nullptr, *bp = nullptr, *cl = nullptr;
+        void *fl = nullptr, *bp = nullptr, *cl = nullptr, *bi = nullptr, *stp = nullptr, *lb = nullptr;
         if (!rc1) { pl->pscan_bufs.push_back(q); rc1 = pool_alloc(ctx, nb * 8 + 8, &b); }
         if (!rc1) { pl->pscan_bufs.push_back(b); rc1 = pool_alloc(ctx, n + 16, &fl); }
         if (!rc1) { pl->pscan_bufs.push_back(fl); rc1 = pool_alloc(ctx, n / PS_BLOCK + 16, &bp); }
         if (!rc1) { pl->pscan_bufs.push_back(bp); rc1 = pool_alloc(ctx, n + 16, &cl); }
+        if (!rc1) { pl->pscan_bufs.push_back(cl); rc1 = pool_alloc(ctx, n / PS_BLOCK + 16, &bi); }
+        if (!rc1) { pl->pscan_bufs.push_back(bi); rc1 = pool_alloc(ctx, (n / PS_BLOCK + 16) * 4, &stp); }
+        if (!rc1) { pl->pscan_bufs.push_back(stp); rc1 = pool_alloc(ctx, (n / PS_BLOCK + 16) * 4, &lb); }
         if (rc1) return fail(rc1);
-        pl->pscan_bufs.push_back(cl);
+        pl->pscan_bufs.push_back(lb);
         S.P = (unsigned long long*)p; S.inc = (unsigned long long*)q; S.bsum = (unsigned long long*)b;
         S.sflag = (unsigned char*)fl; S.bpar = (unsigned char*)bp; S.cls = (unsigned char*)cl;
+        S.bpin = (unsigned char*)bi; S.stamp = (uint32_t*)stp; S.lbk = (uint32_t*)lb;
         S.n = U.n_samples;
         S.p0 = (unsigned long long)(U.init_phase * 1099511627776.0f);
         pl->pscans.push_back(S);
@@ -817,23 +821,23 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
         CU(ctx, cudaMemsetAsync(S.status, 0, 64, s));
         const uint32_t n = S.n, nb = (uint32_t)(((uint64_t)n + 1 + SCAN_TILE - 1) / SCAN_TILE);
         const uint32_t g256 = (n + 255) / 256;
-        auto scan = [&](int verify) {
+        auto scan = [&](int verify, uint32_t next_round) {
             k_ps_scan_reduce<<<nb, SCAN_THREADS, 0, s>>>(S);
             k_ps_scan_spine<<<1, 1024, 0, s>>>(S, nb);
-            k_ps_scan_apply<<<nb, SCAN_THREADS, 0, s>>>(S, verify);
+            k_ps_scan_apply<<<nb, SCAN_THREADS, 0, s>>>(S, verify, next_round);
         };
         k_ps_init<<<g256, 256, 0, s>>>(S);
-        scan(0);                                           // round 0: unrounded prefix sum
+        scan(0, 1);                                        // round 0: unrounded prefix sum; every block stamped for round 1
         pl->last_launches += 4;
         // measured: 1-2 rounds at 44 k samples, 3 at 0.4-1.3 M, 5 at 26 M; enqueue about twice that
         int rounds = 4;
         for (uint64_t m = 1ull << 18; m < n && rounds < PS_MAX_ROUNDS; m <<= 1) ++rounds;
         for (int r = 0; r < rounds; ++r) {                 // every kernel returns at once after convergence
             const uint32_t nblk = (n + PS_BLOCK - 1) / PS_BLOCK;
-            k_ps_replay<<<(nblk + 127) / 128, 128, 0, s>>>(S);
+            k_ps_replay<<<(nblk + 127) / 128, 128, 0, s>>>(S, (uint32_t)r + 1u);
             k_ps_parity_spine<<<1, 1024, 0, s>>>(S, nblk);
             k_ps_parity_fix<<<(nblk + 127) / 128, 128, 0, s>>>(S);
-            scan(1);
+            scan(1, (uint32_t)r + 2u);
             k_ps_check<<<1, 1, 0, s>>>(S);
             pl->last_launches += 7;
         }
