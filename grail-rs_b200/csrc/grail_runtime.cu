@@ -605,7 +605,7 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
 
     // ---- long utterances: exact parallel phase scan instead of the serial chain.  The chains of k_phase_pair run
     //      concurrently, so that kernel lasts as long as its longest utterance (4.7 ns/sample measured); a scan costs
-    //      about 0.45 ms of launches plus 0.16 ns/sample and scans run one after another.  Take the k longest
+    //      about 0.40 ms of launches plus 0.125 ns/sample and scans run one after another.  Take the k longest
     //      utterances (k <= 16) that minimise scans + longest remaining chain.
     {
         std::vector<uint32_t> longs;
@@ -616,7 +616,7 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
         for (uint32_t u = 0; u < n_utts; ++u)
             if (pl->utts[u].n_samples < ctx->pscan_min) rest_max = std::max(rest_max, pl->utts[u].n_samples);
         auto chain_ms = [](uint32_t n) { return 4.7e-6 * (double)n; };
-        auto scan_ms = [](uint32_t n) { return 0.45 + 0.16e-6 * (double)n; };
+        auto scan_ms = [](uint32_t n) { return 0.40 + 0.125e-6 * (double)n; };
         size_t best_k = 0;
         double best = chain_ms(longs.empty() ? rest_max : std::max(rest_max, pl->utts[longs[0]].n_samples)), scans = 0.0;
         for (size_t k = 1; k <= longs.size() && k <= 16; ++k) {
