@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgrail_cuda.so")
+LIB_PATH = os.environ.get("GRAIL_CUDA_LIB") or os.path.join(HERE, "libgrail_cuda.so")   # (the override loads experimental builds of the same library)
 NF = 8
 
 ELEM_DT = np.dtype([
@@ -51,7 +51,7 @@ EXPORTS = [
     "grail_cuda_plan_create_phonemes", "grail_cuda_plan_destroy",
     "grail_cuda_plan_join", "grail_cuda_plan_total_samples", "grail_cuda_plan_out_offsets", "grail_cuda_plan_launch", "grail_cuda_plan_launch_interleaved",
     "grail_cuda_plan_device_output", "grail_cuda_plan_read_output", "grail_cuda_plan_timings",
-    "grail_cuda_plan_read_intermediates", "grail_cuda_plan_phase_scan_stats", "grail_cuda_stream_new", "grail_cuda_stream_push",
+    "grail_cuda_plan_read_intermediates", "grail_cuda_plan_phase_scan_stats", "grail_cuda_plan_phase_stats", "grail_cuda_stream_new", "grail_cuda_stream_push",
     "grail_cuda_stream_finish", "grail_cuda_stream_pull", "grail_cuda_stream_free", "grail_cuda_probe_fp32_peak",
     "grail_cuda_debug_clock_desc", "grail_cuda_debug_clock_asc", "grail_cuda_debug_lcg_jump",
     "grail_cuda_debug_jitter_index", "grail_cuda_debug_div_check",
@@ -97,6 +97,7 @@ def lib() -> C.CDLL:
         "grail_cuda_plan_timings": (i32, [vp, C.POINTER(Timings)]),
         "grail_cuda_plan_read_intermediates": (i32, [vp, vp, vp, vp]),
         "grail_cuda_plan_phase_scan_stats": (i32, [vp, vp]),
+        "grail_cuda_plan_phase_stats": (i32, [vp, vp]),
         "grail_cuda_stream_new": (i32, [vp, vp, C.POINTER(vp)]),
         "grail_cuda_stream_push": (i32, [vp, vp, u32]),
         "grail_cuda_stream_finish": (i32, [vp]),

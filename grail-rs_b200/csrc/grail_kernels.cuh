@@ -42,6 +42,7 @@ struct UttDev {
     uint32_t jw0;                  // value-noise wraps that happened before sample 0 (continued streams)
     uint32_t has_init;             // filter states at sample 0 come from PlanDev::utt_init (continued streams)
     uint64_t sample0;              // absolute index of sample 0 in its stream (aspiration-noise draw index)
+    uint32_t pc_first, pc_count;   // this utterance's phase chunks (k_phase_a / k_phase_b), pc_count = ceil(n_samples / phase_chunk)
 };
 
 // phoneme-level input of a plan: Selector and the Intonator stub run on the device
@@ -85,6 +86,13 @@ struct PlanDev {
     const float*        utt_init;  // per utterance 32 floats: a[8], b[8], c[8] at sample 0 (used when has_init)
     float*              utt_final; // per utterance 32 floats: a[8], b[8], c[8] after the last sample, [24] = carrier phase
     const uint32_t*     pscan_status; // 16 words per parallel phase scan: {mismatches, done, rounds, unsupported, history[12]}
+    float*              pchunks;   // chunk-parallel exact phase: per-chunk records, one array per field (grail_phase.cuh; null: serial chains only)
+    uint32_t            pc_stride; // elements per field array
+    double*             bsum;      // sum of F_t over every 256-sample run (k_frequency), the guesses' raw material
+    uint32_t*           utt_status;// per utterance: bit 0 = carrier phase proven exact by the chunk-parallel path
+    uint32_t*           pstats;    // 64 words: see PSTAT_*
+    uint32_t            phase_chunk; // PC, multiple of 256 (0: chunk-parallel path off)
+    uint32_t            n_pchunks;
     uint32_t*           err;       // device error word
     uint32_t n_utts, n_items, n_groups, n_jscheds;
     uint32_t chunk_len;            // CL, multiple of 256
@@ -301,6 +309,7 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
     float nxt = lcg_float(s_next);
 
     float* dst = P.F + U.f_off + ns;
+    double fsum = 0.0;  // exact sum of this run's F_t (every term is a multiple of 2^-40 or so): k_phase_guess's raw material
     bool odd = false;   // any increment that is negative or NaN: k_phase then takes its fully general path
     // one sample of the scalar frequency path, strict ops in the reference's order
     auto freq_sample = [&]() -> float {
@@ -314,6 +323,7 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
         const float n0 = sadd(smul(cur, ssub(1.0f, jph)), smul(nxt, jph));                 // :254
         const float fr = sadd(fb, smul(n0, dfreq));                                        // :763
         odd |= !(fr >= 0.0f);
+        fsum += (double)fr;
         return fr;
     };
     for (uint32_t k0 = 0; k0 < count; k0 += 8) {
@@ -357,6 +367,7 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
         }
     }
     P.fflags[(U.f_off + ns + ((count - 1) & ~127u)) >> 7] = odd ? 1u : 0u;   // the last (possibly partial) 128-block
+    if (P.bsum) P.bsum[(U.f_off + ns) >> 8] = fsum;
     if (it.n0 + it.len == U.n_samples && off + count == it.len) {
         // the lane that wrote the utterance's last sample rounds the row up: k_phase_pair copies F_t in groups of 8
         // and the flag words in pairs, so nothing it touches is left unwritten (the values themselves are unused)
@@ -555,6 +566,7 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
     const uint32_t n = U.n_samples;
     if (n == 0) return;
     if (U.pscan >= 0 && P.pscan_status[16 * U.pscan + 1] != 0u) return;   // the exact parallel scan already did it
+    if (P.pchunks && (P.utt_status[u] & 1u)) return;                       // the chunk-parallel path proved it (grail_phase.cuh)
     const uint32_t ntiles = (n + PH_TILE - 1) / PH_TILE;
     const unsigned full_a = (unsigned)__cvta_generic_to_shared(&s_full[slot][0]);     // + 8 * buf
     const unsigned empty_a = (unsigned)__cvta_generic_to_shared(&s_empty[slot][0]);
@@ -1742,3 +1754,5 @@ __global__ void __launch_bounds__(256) k_probe_mufu(float* sink, int iters, floa
 }
 
 } // namespace grail
+
+#include "grail_phase.cuh"

@@ -49,6 +49,9 @@ struct grail_ctx {
     int pscan_cost_model = 1;        // 0: scan every utterance >= pscan_min (at most 16), whatever it costs
     int      zero_copy_out = 0;      // 1: k_formant stores straight into pinned host output (measured slower: 23 vs 50 GB/s over PCIe)
     int      formants_per_lane = 2;  // 1 or 2 formants of an utterance share one lane's clocks, noise and saw
+    int      phase_mode = 1;         // 1: chunk-parallel exact carrier phase (grail_phase.cuh); 0: serial chains (+ phase scan for long utterances)
+    uint32_t phase_chunk = 2048;     // samples per phase chunk (multiple of 256)
+    int      phase_rounds = -1;      // repair rounds enqueued after the first proof (-1: by the longest utterance)
     // pinned staging for pageable D2H
     void*    stage[2] = { nullptr, nullptr };
     size_t   stage_bytes = 0;
@@ -154,6 +157,8 @@ struct grail_plan {
     std::vector<PScanDev> pscans;          // exact parallel phase scans (one per long utterance)
     std::vector<uint32_t> pscan_utt;
     uint32_t* d_pscan_status = nullptr;
+    float* d_pchunks = nullptr; uint32_t pc_stride = 0; double* d_bsum = nullptr; uint32_t* d_utt_status = nullptr; uint32_t* d_pstats = nullptr;
+    uint32_t n_pchunks = 0, phase_chunk = 0, max_pchunks = 0;   // phase_chunk == 0: serial chains only
     bool select_on_device = false;   // d_elems was written by k_select from phoneme-level input
     std::vector<void*> pscan_bufs;
     bool jit_on_host = false;   // few distinct jitter increments: schedules computed by the planner
@@ -371,6 +376,13 @@ static PlanDev plan_dev(const grail_plan* pl, bool with_dbg, int slot = 0)
     P.pscan_status = pl->d_pscan_status;
     P.utt_init = pl->d_utt_init;
     P.utt_final = pl->d_utt_final;
+    P.pchunks = pl->phase_chunk ? pl->d_pchunks : nullptr;
+    P.bsum = pl->phase_chunk ? pl->d_bsum : nullptr;
+    P.utt_status = pl->d_utt_status;
+    P.pstats = pl->d_pstats;
+    P.phase_chunk = pl->phase_chunk;
+    P.n_pchunks = pl->n_pchunks;
+    P.pc_stride = pl->pc_stride;
     P.n_utts = pl->n_utts; P.n_items = pl->n_items; P.n_groups = pl->n_groups; P.n_jscheds = pl->n_jscheds;
     P.chunk_len = pl->chunk_len;
     P.out_channels = pl->out_channels;
@@ -383,7 +395,8 @@ static void plan_release(grail_plan* pl)
     if (!pl) return;
     grail_ctx* ctx = pl->ctx;
     void* bufs[] = { pl->d_elems, pl->d_segs, pl->d_utts, pl->d_items, pl->d_jscheds, pl->d_jrecs, pl->d_F, pl->d_saw,
-                     pl->d_phase_dbg, pl->d_err, pl->d_out, pl->d_fflags, pl->d_utt_init, pl->d_utt_final };
+                     pl->d_phase_dbg, pl->d_err, pl->d_out, pl->d_fflags, pl->d_utt_init, pl->d_utt_final,
+                     pl->d_pchunks, pl->d_bsum, pl->d_utt_status, pl->d_pstats };
     for (void* b : bufs) pool_free(ctx, b);
     for (void* b : pl->pscan_bufs) pool_free(ctx, b);
     pool_free(ctx, pl->slot[1].F); pool_free(ctx, pl->slot[1].fflags); pool_free(ctx, pl->slot[1].saw);
@@ -485,6 +498,23 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
     }
     pl->total_samples = total;
     pl->f_words = f_words + 256;
+    // chunk-parallel exact phase: chunks of PC samples, numbered utterance by utterance
+    pl->phase_chunk = ctx->phase_mode ? std::max<uint32_t>(256u, (ctx->phase_chunk + 255u) & ~255u) : 0u;
+    if (pl->phase_chunk) {
+        uint64_t npc = 0;
+        for (uint32_t u = 0; u < n_utts; ++u) {
+            UttDev& U = pl->utts[u];
+            U.pc_first = (uint32_t)npc;
+            U.pc_count = (U.n_samples + pl->phase_chunk - 1) / pl->phase_chunk;
+            npc += U.pc_count;
+            pl->max_pchunks = std::max(pl->max_pchunks, U.pc_count);
+        }
+        if (npc > 0xFFFFFFF0ull) {
+            plan_release(pl);
+            return set_err(ctx, GRAIL_ERR_UNSUPPORTED, "too many phase chunks");
+        }
+        pl->n_pchunks = (uint32_t)npc;
+    }
     pl->fpt = (uint32_t)ctx->formants_per_lane;
     pl->nw = (nw + pl->fpt - 1) / pl->fpt;   // warps per CTA: ceil(active formants / formants per lane)
     nw = pl->nw;
@@ -609,7 +639,7 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
     //      utterances (k <= 16) that minimise scans + longest remaining chain.
     {
         std::vector<uint32_t> longs;
-        for (uint32_t u = 0; u < n_utts; ++u)
+        for (uint32_t u = 0; u < n_utts && !pl->phase_chunk; ++u)   // (the chunk-parallel path needs no special case for them)
             if (pl->utts[u].n_samples >= ctx->pscan_min) longs.push_back(u);
         std::sort(longs.begin(), longs.end(), [&](uint32_t a, uint32_t b) { return pl->utts[a].n_samples > pl->utts[b].n_samples; });
         uint32_t rest_max = 0;                           // longest utterance below the threshold
@@ -661,6 +691,13 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
     PA(pl->d_utt_final, std::max<size_t>(n_utts, 1) * 32 * sizeof(float));
     PA(pl->d_utt_init, std::max<size_t>(n_utts, 1) * 32 * sizeof(float));
     PA(pl->d_pscan_status, 256 + 64 * pl->pscan_utt.size());
+    PA(pl->d_utt_status, std::max<size_t>(n_utts, 1) * sizeof(uint32_t));
+    PA(pl->d_pstats, 256);
+    if (pl->phase_chunk) {
+        pl->pc_stride = (pl->n_pchunks + 64u) & ~31u;
+        PA(pl->d_pchunks, (size_t)pl->pc_stride * PCF_COUNT * sizeof(float));
+        PA(pl->d_bsum, (pl->f_words / 256 + 2) * sizeof(double));
+    }
     for (uint32_t u : pl->pscan_utt) {
         const UttDev& U = pl->utts[u];
         PScanDev S;
@@ -730,6 +767,8 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
         if (ss && ss->filter_state) memcpy(init, ss->filter_state, 24 * sizeof(float));
         CUF(cudaMemsetAsync(pl->d_utt_init, 0, std::max<size_t>(n_utts, 1) * 32 * sizeof(float), s));
         CUF(cudaMemsetAsync(pl->d_utt_final, 0, std::max<size_t>(n_utts, 1) * 32 * sizeof(float), s));
+        CUF(cudaMemsetAsync(pl->d_utt_status, 0, std::max<size_t>(n_utts, 1) * sizeof(uint32_t), s));
+        CUF(cudaMemsetAsync(pl->d_pstats, 0, 256, s));
         if (ss) {   // formants nobody touches in this window keep their carried state
             CUF(cudaMemcpyAsync(pl->d_utt_init, init, sizeof init, cudaMemcpyHostToDevice, s));
             CUF(cudaMemcpyAsync(pl->d_utt_final, init, sizeof init, cudaMemcpyHostToDevice, s));
@@ -842,6 +881,33 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
             pl->last_launches += 7;
         }
         k_ps_saw<<<((n + 7) / 8 + 255) / 256, 256, 0, s>>>(S, P, u);
+        pl->last_launches++;
+    }
+    if (pl->n_items && pl->phase_chunk) {
+        // chunk-parallel exact phase (grail_phase.cuh): guess, round A, scan, round B, then proof / repair rounds
+        const unsigned wg = (unsigned)(((uint64_t)pl->n_utts * 32 + 127) / 128), cg = (pl->n_pchunks + 127) / 128;
+        CU(ctx, cudaMemsetAsync(pl->d_pstats, 0, 256, s));
+        k_phase_guess<<<wg, 128, 0, s>>>(P);
+        pl->last_launches++;
+        if (pl->max_pchunks > 1) {
+            k_phase_a<<<cg, 128, 0, s>>>(P);
+            k_phase_scan_a<<<wg, 128, 0, s>>>(P);
+            pl->last_launches += 2;
+        }
+        k_phase_b<<<cg, 128, 0, s>>>(P, 0u);
+        pl->last_launches++;
+        // repair rounds: a handful for seconds of speech, a few more for long forms (the guesses drift with the square
+        // root of the length, and every round's corrections are an order of magnitude smaller than the last)
+        int rounds = 4;
+        for (uint32_t m = 256; m < pl->max_pchunks && rounds < PH_MAX_ROUNDS; m <<= 1) ++rounds;
+        if (ctx->phase_rounds >= 0) rounds = std::min(ctx->phase_rounds, (int)PH_MAX_ROUNDS);
+        if (pl->max_pchunks <= 1) rounds = 0;
+        for (int r = 1; r <= rounds; ++r) {
+            k_phase_fix<<<wg, 128, 0, s>>>(P, (uint32_t)r);
+            k_phase_b<<<cg, 128, 0, s>>>(P, (uint32_t)r);
+            pl->last_launches += 2;
+        }
+        k_phase_fix<<<wg, 128, 0, s>>>(P, (uint32_t)PH_MAX_ROUNDS + 1u);   // the final proof: sets the status bits
         pl->last_launches++;
     }
     if (pl->n_items) {
@@ -1001,6 +1067,13 @@ int grail_cuda_set_option(grail_ctx* ctx, const char* key, double value)
         ctx->pipeline = value != 0.0;
     } else if (!strcmp(key, "phase_lean")) {
         ctx->phase_lean = value < 0.0 ? -1 : (value != 0.0);
+    } else if (!strcmp(key, "phase_mode")) {
+        ctx->phase_mode = value != 0.0;
+    } else if (!strcmp(key, "phase_chunk")) {
+        if (!(value >= 256.0 && value <= 1048576.0)) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "phase_chunk out of range [256, 2^20]");
+        ctx->phase_chunk = (uint32_t)value;
+    } else if (!strcmp(key, "phase_rounds")) {
+        ctx->phase_rounds = value < 0.0 ? -1 : (value > PH_MAX_ROUNDS ? PH_MAX_ROUNDS : (int)value);
     } else if (!strcmp(key, "interleave")) {
         ctx->interleave = value != 0.0;
     } else if (!strcmp(key, "pscan_cost_model")) {
@@ -1218,6 +1291,26 @@ int grail_cuda_plan_phase_scan_stats(grail_plan* plan, uint32_t* stats)
             fprintf(stderr, "\n");
         }
     }
+    return GRAIL_OK;
+}
+
+int grail_cuda_plan_phase_stats(grail_plan* plan, uint32_t* stats)
+{
+    if (!plan || !stats) return GRAIL_ERR_INVALID_ARG;
+    grail_ctx* ctx = plan->ctx;
+    memset(stats, 0, 8 * sizeof(uint32_t));
+    stats[0] = plan->n_pchunks;
+    stats[5] = plan->phase_chunk;
+    if (!plan->phase_chunk || !plan->launched) return GRAIL_OK;
+    int rcj = plan_join(plan);
+    if (rcj) return rcj;
+    uint32_t st[16];
+    CU(ctx, cudaMemcpyAsync(st, plan->d_pstats, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    stats[1] = st[PSTAT_WALKS];
+    stats[2] = st[PSTAT_UNPROVEN];
+    stats[3] = st[PSTAT_ROUNDS];
+    stats[4] = st[PSTAT_MISMATCH];
     return GRAIL_OK;
 }
 

@@ -330,6 +330,13 @@ class Plan:
         self.ctx._check(self._L.grail_cuda_plan_phase_scan_stats(self._h, ptr(st)))
         return {"scans": int(st[0]), "converged": int(st[1]), "max_rounds": int(st[2]), "refused": int(st[3])}
 
+    def phase_stats(self) -> dict:
+        """chunk-parallel exact carrier phase of the last launch (grail_cuda_plan_phase_stats)"""
+        st = np.zeros(8, np.uint32)
+        self.ctx._check(self._L.grail_cuda_plan_phase_stats(self._h, ptr(st)))
+        return {"chunks": int(st[0]), "walks": int(st[1]), "unproven_utterances": int(st[2]), "repair_rounds": int(st[3]),
+                "failed_boundaries": int(st[4]), "phase_chunk": int(st[5])}
+
     def read_intermediates(self):
         """bit-exact taps: (F_t, carrier phase before each sample, polyBLEP saw), packed like the output"""
         n = self.total_samples

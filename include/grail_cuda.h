@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 #define GRAIL_NUM_FORMANTS 8 /* reference NUM_FORMANTS, src/lib.rs:24 */
-#define GRAIL_ABI_VERSION 2   /* 2: phoneme-level plans, grail_cuda_transcribe_batch */
+#define GRAIL_ABI_VERSION 3   /* 2: phoneme-level plans, grail_cuda_transcribe_batch; 3: grail_cuda_plan_phase_stats */
 
 typedef enum grail_status {
     GRAIL_OK = 0,
@@ -212,6 +212,15 @@ int  grail_cuda_plan_timings(const grail_plan* plan, grail_timings* out);
  * to the serial chain), largest number of refinement rounds used, scans refused (an F_t outside [2^-16, 0.5])}
  * for the most recent launch. */
 int  grail_cuda_plan_phase_scan_stats(grail_plan* plan, uint32_t* stats);
+/* The carrier phase (src/lib.rs:520-525) is computed exactly AND in parallel over time chunks of option "phase_chunk"
+ * samples (default 2048; option "phase_mode" = 0 falls back to one serial chain per utterance): every chunk is walked
+ * from a start phase derived from its neighbours, and the result is accepted only when each chunk's end equals the
+ * next chunk's start bit for bit (a proof by induction from the exact phase at sample 0); mismatching chunks are
+ * shifted and walked again for up to option "phase_rounds" rounds, and an utterance that is still unproven then gets the
+ * serial chain.  stats[8] of the most recent launch = {phase chunks in the plan, chunks walked in all rounds together,
+ * utterances that fell back to the serial chain, last repair round that was needed (0 = none), chunk boundaries that
+ * failed a proof, phase_chunk, 0, 0}. */
+int  grail_cuda_plan_phase_stats(grail_plan* plan, uint32_t* stats);
 /* debug / parity taps, host buffers of total_samples entries; any may be NULL:
  * the bit-exact fundamental F_t, the carrier phase BEFORE each sample, and the polyBLEP saw */
 int  grail_cuda_plan_read_intermediates(grail_plan* plan, float* frequency, float* carrier_phase, float* saw);
