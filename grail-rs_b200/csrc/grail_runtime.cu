@@ -49,7 +49,7 @@ struct grail_ctx {
     int pscan_cost_model = 1;        // 0: scan every utterance >= pscan_min (at most 16), whatever it costs
     int      zero_copy_out = 0;      // 1: k_formant stores straight into pinned host output (measured slower: 23 vs 50 GB/s over PCIe)
     int      formants_per_lane = 2;  // 1 or 2 formants of an utterance share one lane's clocks, noise and saw
-    int      phase_mode = 1;         // 1: chunk-parallel exact carrier phase (grail_phase.cuh); 0: serial chains (+ phase scan for long utterances)
+    int      phase_mode = 0;         // 1: chunk-parallel exact carrier phase (grail_phase.cuh); 0: serial chains (+ phase scan for long utterances)
     uint32_t phase_chunk = 2048;     // samples per phase chunk (multiple of 256)
     int      phase_rounds = -1;      // repair rounds enqueued after the first proof (-1: by the longest utterance)
     // pinned staging for pageable D2H
