@@ -1,18 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the grail-rs waveform path on B200 (contract: see the task statement).
+"""bench.py -- benchmarks of the grail-rs waveform path on B200 (contract: see the task statement).
 
 A "step" is one pass of the hot path (Sequencer -> Jitter -> Synthesize) over one batch of synthetic phoneme
-sequences.  At N GPUs every rank owns one BASELINE config-2 batch (1 024 utterances x 10 phonemes, ~5 s each,
-default voice, 44.1 kHz, jitter_seed = global utterance index): utterances are independent, so the path shards by
-utterance with no data-path collective ("scaling": "weak").
+sequences.  `--config` picks the BASELINE.json workload (the headline, and the default, is config 2):
+
+  2  batch of 1 024 utterances x 10 phonemes (~5 s), default voice, 44.1 kHz per GPU ("scaling": "weak": utterances
+     are independent, every rank owns one such batch, no data-path collective)
+  3  one 10-minute utterance (26 457 161 samples): the parallel-in-time path; does not shard (N > 1: replicas)
+  4  65 536 short utterances with per-utterance random voices, ONE fixed batch split over the ranks by LPT on the exact
+     sample counts ("scaling": "strong"); optional NCCL gather of the outputs into batch order (--gather 1), per-rank
+     load imbalance and a parity block against the oracle
+  5  the config-2 shape at 16 / 22.05 / 44.1 / 48 kHz, one line with a table: GPU samples/s and host-CPU samples/s per rate
 
   value  = samples/s, whole job, inputs (phoneme tables, schedules, work items) already resident in HBM
   e2e    = the same metric through the C-ABI call a reference user would make (grail_cuda_synthesize_batch):
            host phoneme records in, host (pinned) f32 samples out, H2D + D2H inside the timed region
-  roofline / cpu_baseline: see DESIGN.md
+  roofline / cpu_baseline: see DESIGN.md section 6
 
-  --impl reference  times the reference's own CPU algorithm (the oracle restatement, all host threads) on a
-                    bounded sample of the same workload.
+  --impl reference  times the reference's own CPU algorithm (the oracle restatement, all host threads) on the same
+                    workload, whole batch per step.
 """
 from __future__ import annotations
 
@@ -35,6 +41,8 @@ UNIT = "samples/s"
 SAMPLE_RATE = 44100.0
 N_UTTS = 1024
 N_PHONEMES = 10
+N_UTTS_CONFIG4 = 65536
+RATES_CONFIG5 = (16000.0, 22050.0, 44100.0, 48000.0)
 # algorithmic f32 flops per sample, as written in the reference: whole path, and the share the
 # dominant kernel (k_formant) covers = everything but the scalar frequency/phase lane (26 flops)
 FLOPS_PER_SAMPLE = 762
@@ -42,9 +50,10 @@ FLOPS_PER_SAMPLE_FORMANT = 736
 # the same count when the formants whose amplitude is zero in every phoneme are left out, as the reference's result
 # allows (about 400 for the default voice's 4 active formants, minus the 26 of the frequency lane)
 FLOPS_PER_SAMPLE_FORMANT_ACTIVE = 374
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_formant launch on this workload, from the committed
-# `ncu --set full` capture (profiles/r1_k_formant_ncu_full.txt: 1.567 GB read + 0.868 GB written; algorithmic 1.806 GB)
-NCU_TRAFFIC_BYTES = 1373045000 + 862064384
+# What the kernels EXECUTE per config-2 launch (thread-level FP32 operations from the SASS opcode histogram of an
+# `ncu --set full --import-source on` capture, FFMA = 2 flops, FFMA2 = 4, FADD2 / FMUL2 = 2) and the DRAM bytes ncu saw:
+# written by scripts/roofline_from_ncu.py from the round's own capture, never typed in by hand.
+ROOFLINE_FILE = os.path.join(ROOT, "profiles", "r2_roofline_inputs.json")
 
 
 def host_cores() -> int:
@@ -54,10 +63,9 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
-def workload(rank: int, n_utts: int = N_UTTS):
-    import grail_rs_b200 as g
+def workload_config2(rank: int, n_utts: int = N_UTTS, sample_rate: float = SAMPLE_RATE):
     from grail_rs_b200 import workloads as W
-    elems, offs, vp = W.config2(n_utts, N_PHONEMES, SAMPLE_RATE)
+    elems, offs, vp = W.config2(n_utts, N_PHONEMES, sample_rate)
     vp = vp.copy()
     vp["jitter_seed"] = (np.arange(n_utts) + rank * n_utts).astype(np.uint32)
     return elems, offs, vp
@@ -121,6 +129,13 @@ def measured_peaks() -> dict:
         return {}
 
 
+def roofline_inputs() -> dict:
+    try:
+        return json.load(open(ROOFLINE_FILE))
+    except Exception:
+        return {}
+
+
 def bind_to_gpu_cpus(device_index: int):
     """pin the calling process to the CPUs NVML reports as local to the GPU; returns the mask size or None"""
     try:
@@ -139,17 +154,50 @@ def bind_to_gpu_cpus(device_index: int):
     return None
 
 
-def cpu_baseline_run(n_utts: int, threads: int, rank: int = 0):
-    """the reference's CPU algorithm (oracle restatement, -O3 strict f32) over `threads` host threads"""
+_COUNT_CACHE: dict = {}
+
+
+def cpu_run(elems, offs, vp, threads: int):
+    """the reference's CPU algorithm (oracle restatement, -O3 strict f32), one utterance per task on `threads` host
+    threads; returns (samples, seconds)"""
     from oracle import oracle as O
-    elems, offs, vp = workload(rank, n_utts)
-    counts = np.full(n_utts, 220476, np.uint64)
+    # the oracle's own sample counts (nothing of the product on this path), memoised per (phoneme lengths, rate)
+    counts = np.empty(len(offs) - 1, np.uint64)
+    for u in range(len(offs) - 1):
+        e = elems[offs[u]:offs[u + 1]]
+        key = (e["length"].tobytes(), float(vp[u]["sample_rate"]))
+        if key not in _COUNT_CACHE:
+            _COUNT_CACHE[key] = O.count_samples(e, float(vp[u]["sample_rate"]))
+        counts[u] = _COUNT_CACHE[key]
     oo = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint64)
     out = np.empty(int(oo[-1]), np.float32)
     t0 = time.perf_counter()
     O.synthesize_batch(elems, offs, vp, out_offsets=oo, n_threads=threads, o3=True, out=out)
-    dt = time.perf_counter() - t0
-    return int(oo[-1]), dt
+    return int(oo[-1]), time.perf_counter() - t0
+
+
+def config_workload(config: int, rank: int, world: int):
+    """(elems, offs, vp, description, scaling, extra) of this rank's share of the workload"""
+    from grail_rs_b200 import workloads as W
+    if config == 2:
+        e, o, v = workload_config2(rank)
+        return e, o, v, (f"config2: {N_UTTS} utterances x {N_PHONEMES} phonemes (~5 s) per GPU, default voice, 44.1 kHz, "
+                         "jitter_seed = utterance index"), "weak", {}
+    if config == 3:
+        e, o, v = W.config3()
+        return e, o, v, "config3: one 10-minute utterance (1 200 phonemes, 26 457 161 samples), default voice, 44.1 kHz; replicas at N > 1", "weak", {}
+    if config == 4:
+        import grail_rs_b200 as g
+        from grail_rs_b200 import sharding
+        e, o, v = W.config4(N_UTTS_CONFIG4)
+        counts = g.count_samples(e, o, v)
+        assign = sharding.lpt_assign(counts, world)
+        se, so, sv = sharding.shard_batch(e, o, v, assign[rank])
+        loads = [int(counts[a].sum()) for a in assign]
+        extra = {"assign": assign, "counts": counts, "full": (e, o, v), "loads": loads}
+        return se, so, sv, (f"config4: {N_UTTS_CONFIG4} utterances x 2-4 phonemes, per-utterance random voice (8 live formants, "
+                            f"pitch, jitter), 44.1 kHz, ONE batch split over {world} GPU(s) by LPT on exact sample counts"), "strong", extra
+    raise ValueError(config)
 
 
 def run_reference(args):
@@ -157,24 +205,36 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = host_cores()
-    n_utts = max(cores, min(N_UTTS, 16 * cores))          # bounded sample: 16 utterances per host thread per step
-    for _ in range(min(args.warmup, 2)):
-        cpu_baseline_run(max(1, n_utts // 4), cores)
+    if args.config == 5:
+        return run_reference_config5(args, cores)
+    elems, offs, vp, desc, scaling, extra = config_workload(args.config, 0, 1)
+    if args.config == 4:
+        # bounded sample of the 65 536 utterances: every 16th (4 096 utterances, 2.7e8 samples) per step
+        from grail_rs_b200 import sharding
+        e, o, v = extra["full"]
+        elems, offs, vp = sharding.shard_batch(e, o, v, np.arange(0, N_UTTS_CONFIG4, 16))
+        sample = "every 16th of the 65 536 config-4 utterances per step"
+    elif args.config == 3:
+        cores = 1
+        sample = "the whole utterance, one core (a single chain does not parallelise on the CPU)"
+    else:
+        sample = f"all {N_UTTS} config-2 utterances per step"
+    if args.warmup and len(offs) - 1 > cores:          # page the library and the thread pool in on a few utterances
+        from grail_rs_b200 import sharding
+        cpu_run(*sharding.shard_batch(elems, offs, vp, np.arange(cores)), cores)
     total, secs = 0, 0.0
     for _ in range(args.steps):
-        n, dt = cpu_baseline_run(n_utts, cores)
+        n, dt = cpu_run(elems, offs, vp, cores)
         total += n
         secs += dt
     v = total / secs
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"config2: {N_UTTS} utterances x {N_PHONEMES} phonemes (~5 s), default voice, 44.1 kHz",
-                   "l2": "inputs larger than L2"},
+        "config": {"workload": desc, "l2": "inputs larger than L2"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n_utts} of the {N_UTTS} config-2 utterances per step ({n_utts * 220476} samples), "
-                                   "oracle -O3 strict f32, one utterance per task"},
+                         "sample": f"{sample} ({total // args.steps} samples), oracle -O3 strict f32, one utterance per task"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "rtf": v / SAMPLE_RATE,
     }
@@ -182,43 +242,185 @@ def run_reference(args):
     return 0
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+def run_reference_config5(args, cores):
+    rows, total, secs = [], 0, 0.0
+    for rate in RATES_CONFIG5:
+        e, o, v = workload_config2(0, N_UTTS, rate)
+        n, dt = cpu_run(e, o, v, cores)
+        rows.append({"sample_rate": rate, "cpu_samples_per_s": n / dt, "samples": n})
+        total += n
+        secs += dt
+    v = total / secs
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": 1,
+                      "warmup": 0, "ms_per_step": 1e3 * secs, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "config5: the config-2 shape at 16 / 22.05 / 44.1 / 48 kHz", "rates": rows},
+                      "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                       "sample": "all 1 024 utterances at each of the four rates, once"},
+                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+    return 0
 
-    import grail_rs_b200 as g
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
-    torch.cuda.set_device(local)
-    # NUMA: keep this rank's threads (and therefore its pinned host buffers, which are placed where they are first
-    # touched) on the CPUs next to its GPU; with 8 ranks the 8 concurrent 0.9 GB device-to-host copies otherwise
-    # cross sockets.  The CPU baseline leg widens the mask again.
-    all_cpus = os.sched_getaffinity(0)
-    numa = bind_to_gpu_cpus(local) if world > 1 else None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+class Dist:
+    """rank / world plumbing: NCCL only for barriers, the max-over-ranks timing and the optional output gather"""
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+        torch.cuda.set_device(self.local)
+        # NUMA: keep this rank's threads (and therefore its pinned host buffers, which are placed where they are first
+        # touched) on the CPUs next to its GPU; the CPU baseline leg widens the mask again.
+        self.all_cpus = os.sched_getaffinity(0)
+        self.numa = bind_to_gpu_cpus(self.local) if self.world > 1 else None
+        if self.world > 1:
+            import torch.distributed as dist
+            self.dist = dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
 
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max(self, x: float) -> float:
+        if self.world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    ctx = g.Context(local)
-    stream = torch.cuda.ExternalStream(ctx.stream_handle, device=torch.device("cuda", local))
-    elems, offs, vp = workload(rank)
-    # consecutive launches of the resident plan overlap: step i+1's frequency / phase kernels (latency-bound) run on a
-    # second stream and scratch set under step i's formant kernel (library option "pipeline"; same bits)
+    def sum(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def timed_resident(D: Dist, ctx, plan, d_out, steps: int, warmup: int, sampler=None):
+    """W warm-up launches, then exactly `steps` launches of the resident plan between two events on the library's
+    stream, barrier + synchronize on both sides; returns (ms max over ranks, wall t0, wall t1)"""
+    torch = D.torch
+    stream = torch.cuda.ExternalStream(ctx.stream_handle, device=torch.device("cuda", D.local))
+    for _ in range(max(warmup, 3)):
+        plan.launch(d_out)
+    plan.join()
+    ctx.synchronize()
+    if sampler is not None:
+        sampler.start()
+        time.sleep(0.25)
+    D.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record(stream)
+    for _ in range(steps):
+        plan.launch(d_out)
+    plan.join()                      # the main stream waits for pipelined launches before the end event
+    e1.record(stream)
+    e1.synchronize()
+    D.barrier()
+    t1 = time.time()
+    return D.max(e0.elapsed_time(e1)), t0, t1
+
+
+def kernel_split(ctx, plan, d_out, reps: int):
+    """per-kernel CUDA-event times of single launches (events inside the library, same stream), averaged"""
+    kern = {"frequency_ms": 0.0, "phase_ms": 0.0, "formant_ms": 0.0, "schedule_ms": 0.0, "total_ms": 0.0}
+    for _ in range(reps):
+        plan.launch(d_out)
+        ctx.synchronize()
+        t = plan.timings()
+        for k in kern:
+            kern[k] += t[k] / reps
+    return kern
+
+
+def roofline_block(ctx, n_samples: int, kern: dict, step_ms: float, config: int) -> dict:
+    """the dominant kernel (k_formant) against the FP32 pipe: executed flops from the round's ncu capture (config 2 only,
+    where the capture was taken), the as-written / live-formant algorithmic counts as separate named fields"""
+    probe = ctx.probe_fp32_peak()
+    peaks = measured_peaks()
+    ri = roofline_inputs() if config == 2 else {}
+    peak_tf = probe["ffma_flops"] / 1e12
+    f_ms = kern["formant_ms"]
+    as_written = FLOPS_PER_SAMPLE_FORMANT * n_samples / (f_ms * 1e-3) / 1e12
+    live = FLOPS_PER_SAMPLE_FORMANT_ACTIVE * n_samples / (f_ms * 1e-3) / 1e12
+    kf = ri.get("k_formant", {})
+    executed = kf.get("executed_flops_per_launch")
+    achieved = executed / (f_ms * 1e-3) / 1e12 if executed else None
+    hbm_bytes = 4 * n_samples * 2          # saw read + f32 samples written (algorithmic bytes of k_formant)
+    step_exec = ri.get("step_executed_flops")
+    out = {
+        "kernel": "k_formant", "bound": "fp32",
+        "achieved": achieved if achieved is not None else live, "peak": peak_tf, "unit": "TFLOP/s",
+        "frac": (achieved if achieved is not None else live) / peak_tf,
+        "achieved_is": ("FP32 operations the kernel EXECUTES per launch (SASS opcode histogram of the committed ncu capture, "
+                        f"{ROOFLINE_FILE.replace(ROOT + '/', '')}) / launch time measured here") if achieved is not None
+                       else "algorithmic flops of the live formants (no ncu capture for this workload)",
+        "traffic": kf.get("dram_bytes_per_launch"),
+        "peak_source": "FFMA issue-rate probe measured live in this run (MEASURED_PEAKS.json has no fp32 figure)",
+        "launch_ms": f_ms,
+        "as_written": {"flops_per_sample": FLOPS_PER_SAMPLE_FORMANT, "tflops": as_written, "frac": as_written / peak_tf,
+                       "note": "SURVEY 8d count of the reference's source; exceeds 1 because zero-amplitude formants are skipped and "
+                               "coefficients are interpolated over 16-sample blocks: NOT a utilisation figure"},
+        "live_formants": {"flops_per_sample": FLOPS_PER_SAMPLE_FORMANT_ACTIVE, "tflops": live, "frac": live / peak_tf},
+        "whole_step": {"ms": step_ms, "as_written_frac": FLOPS_PER_SAMPLE * n_samples / (step_ms * 1e-3) / 1e12 / peak_tf,
+                       "executed_frac": (step_exec / (step_ms * 1e-3) / 1e12 / peak_tf) if step_exec else None},
+        "issue_slots_busy_ncu": kf.get("issue_slots_busy_pct"), "fma_pipe_busy_ncu": kf.get("fma_pipe_busy_pct"),
+        "mufu_peak_per_s": probe["mufu_ops"],
+        "hbm": {"achieved": hbm_bytes / (f_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                "frac": (hbm_bytes / (f_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
+                "peak_source": "MEASURED_PEAKS.json (measured)" if peaks.get("hbm_gbs") else "absent"},
+    }
+    return out
+
+
+def parity_block(ctx, plan, out_t, elems, offs, vp, n_check: int) -> dict:
+    """n_check utterances of this rank's shard against the oracle (audio within tolerance); counts exact for ALL"""
+    from oracle import oracle as O
+    from grail_rs_b200 import sharding
+    from grail_rs_b200 import workloads as W
+    import grail_rs_b200 as g
+    n = len(offs) - 1
+    oo = plan.out_offsets
+    counts = g.count_samples(elems, offs, vp)
+    counts_ok = bool(np.array_equal(np.diff(oo.astype(np.int64)), counts.astype(np.int64)))
+    pick = np.unique(np.linspace(0, n - 1, min(n, n_check)).astype(np.int64))
+    se, so, sv = sharding.shard_batch(elems, offs, vp, pick)
+    want, woo, wc = O.synthesize_batch(se, so, sv, n_threads=host_cores())
+    counts_ok &= bool(np.array_equal(wc.astype(np.int64), counts[pick].astype(np.int64)))
+    worst = {"max_abs": 0.0, "snr_db": float("inf")}
+    for k, u in enumerate(pick.tolist()):
+        got = out_t[int(oo[u]):int(oo[u + 1])].cpu().numpy()
+        st = W.parity_stats(got, want[int(woo[k]):int(woo[k + 1])])
+        worst["max_abs"] = max(worst["max_abs"], st["max_abs"])
+        worst["snr_db"] = min(worst["snr_db"], st["snr_db"])
+    return {"utterances_checked": int(len(pick)), "counts_bit_exact_all": counts_ok, "max_abs": worst["max_abs"],
+            "snr_db": worst["snr_db"], "within_tolerance": bool(worst["max_abs"] <= 1e-4 and worst["snr_db"] >= 90.0),
+            "phase_unproven_utterances": plan.phase_stats()["unproven_utterances"]}
+
+
+def run_ours(args):
+    if args.config == 5:
+        return run_ours_config5(args)
+    D = Dist()
+    torch = D.torch
+    import grail_rs_b200 as g
+    rank, world = D.rank, D.world
+    ctx = g.Context(D.local)
+    elems, offs, vp, desc, scaling, extra = config_workload(args.config, rank, world)
+    # consecutive launches of the resident plan overlap: step i+1's frequency / phase kernels run on a second stream
+    # and scratch set under step i's formant kernel (library option "pipeline"; same bits)
     ctx.set_option("pipeline", 1 if args.pipeline else 0)
     plan = ctx.plan(elems, offs, vp)
     ctx.set_option("pipeline", 0)
@@ -227,132 +429,186 @@ def run_ours(args):
     d_out = out.data_ptr()
 
     # ---------------- device-resident throughput ("value") ----------------
-    for _ in range(max(args.warmup, 3)):
-        plan.launch(d_out)
-    ctx.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kern = {"frequency_ms": 0.0, "phase_ms": 0.0, "formant_ms": 0.0, "schedule_ms": 0.0}
-    t_wall0 = time.time()
-    e0.record(stream)
-    launches = 0
-    for _ in range(args.steps):
-        plan.launch(d_out)
-        launches += 3
-    plan.join()                      # the main stream waits for the pipelined launches before the end event
-    e1.record(stream)
-    e1.synchronize()
-    barrier()
-    t_wall1 = time.time()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    # per-kernel split of the last step (CUDA events inside the library, same stream)
-    tm = plan.timings()
-    launches = tm["n_launches"] * args.steps
+    sampler = ClockSampler(D.local) if rank == 0 else None
+    ms, t_wall0, t_wall1 = timed_resident(D, ctx, plan, d_out, args.steps, args.warmup, sampler)
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    value = world * n_samples * args.steps / (ms * 1e-3)
+    total_samples = D.sum(float(n_samples))          # all ranks (config 2: N x the batch; config 4: the one batch)
+    value = total_samples * args.steps / (ms * 1e-3)
+    reps = max(3, min(args.steps, 10))
+    kern = kernel_split(ctx, plan, d_out, reps)
+    launches = plan.timings()["n_launches"] * args.steps
+    pstats = plan.phase_stats()
 
-    # formant-kernel launch duration averaged over its own timed loop (events around each launch, same stream)
-    f_ms = []
-    for _ in range(max(3, min(args.steps, 10))):
-        plan.launch(d_out)
-        ctx.synchronize()
-        t = plan.timings()
-        f_ms.append(t["formant_ms"])
-        for k in kern:
-            kern[k] += t[k] / max(3, min(args.steps, 10))
-    formant_ms = float(np.mean(f_ms))
+    # ---------------- config 4: imbalance, parity block, optional NCCL gather ----------------
+    cfg4 = None
+    if args.config == 4:
+        from grail_rs_b200 import sharding
+        loads = extra["loads"]
+        par = parity_block(ctx, plan, out, elems, offs, vp, args.parity_utts)
+        par_all = {"within_tolerance": bool(D.sum(0.0 if par["within_tolerance"] and par["counts_bit_exact_all"] else 1.0) == 0.0),
+                   "max_abs": D.max(par["max_abs"]), "snr_db": -D.max(-par["snr_db"]),
+                   "utterances_checked": int(D.sum(par["utterances_checked"])), "per_rank": par["utterances_checked"]}
+        cfg4 = {"load_imbalance_max_over_mean": max(loads) / (sum(loads) / len(loads)), "samples_per_rank": loads,
+                "parity": par_all}
+        if args.gather and world > 1:
+            D.barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            full = sharding.gather_outputs(out, extra["counts"][extra["assign"][rank]], extra["assign"], extra["counts"], ctx=ctx)
+            g1.record()
+            torch.cuda.synchronize()
+            gather_ms = D.max(g0.elapsed_time(g1))
+            # every rank's piece sits where batch order says, bit for bit
+            all_off = np.concatenate([[0], np.cumsum(extra["counts"].astype(np.int64))])
+            mine = extra["assign"][rank]
+            oo = plan.out_offsets
+            ok = True
+            for k in np.unique(np.linspace(0, len(mine) - 1, 64).astype(np.int64)).tolist():
+                u = int(mine[k])
+                ok &= bool(torch.equal(full[all_off[u]:all_off[u + 1]], out[int(oo[k]):int(oo[k + 1])]))
+            cfg4["gather"] = {"ms": gather_ms, "bytes_gathered_per_rank": int(full.numel() * 4),
+                              "gb_per_s_per_rank": full.numel() * 4 / (gather_ms * 1e-3) / 1e9,
+                              "own_pieces_bit_equal": bool(D.sum(0.0 if ok else 1.0) == 0.0),
+                              "checksum": float(full[:: max(1, full.numel() // (1 << 20))].double().abs().sum().item()),
+                              "how": "one NCCL all_gather_into_tensor of padded shards + one grail_cuda_copy_segments launch"}
+            del full
 
     # ---------------- end to end through the C ABI with host buffers ("e2e") ----------------
-    host_out = ctx.pinned_empty(n_samples, np.float32)
-    oo = plan.out_offsets.copy()
-    h2d = elems.nbytes + offs.nbytes + vp.nbytes
-    d2h = n_samples * 4
-    e2e_steps = max(2, min(args.steps, 5))
-    ctx.synthesize_batch(elems, offs, vp, out=host_out, out_offsets=oo)   # warm the buffer pool
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        ctx.synthesize_batch(elems, offs, vp, out=host_out, out_offsets=oo)
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = world * n_samples * e2e_steps / e2e_s
-    checksum = float(np.abs(host_out[: 220476]).sum())
-    # the same call with i16 PCM out (what the reference's WAV path keeps, examples/cli.rs:49-51): half the D2H bytes
-    host_pcm = ctx.pinned_empty(n_samples, np.int16)
-    ctx.synthesize_batch(elems, offs, vp, out=host_pcm, out_offsets=oo, fmt=g.I16)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    e2e = None
+    e2e_i16 = None
+    if n_samples * 4 <= args.e2e_max_gb * (1 << 30):
+        host_out = ctx.pinned_empty(n_samples, np.float32)
+        oo = plan.out_offsets.copy()
+        h2d = elems.nbytes + offs.nbytes + vp.nbytes
+        e2e_steps = max(2, min(args.steps, 5))
+        ctx.synthesize_batch(elems, offs, vp, out=host_out, out_offsets=oo)   # warm the buffer pool
+        D.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.synthesize_batch(elems, offs, vp, out=host_out, out_offsets=oo)
+        D.barrier()
+        e2e_s = D.max(time.perf_counter() - t0)
+        e2e = {"value": total_samples * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(n_samples * 4), "steps": e2e_steps,
+               "api": "grail_cuda_synthesize_batch (host records in, pinned f32 out)", "cpus_bound_per_rank": D.numa}
+        checksum = float(np.abs(host_out[: min(n_samples, 220476)]).sum())
+        # the same call with i16 PCM out (what the reference's WAV path keeps, examples/cli.rs:49-51): half the D2H bytes
+        host_pcm = ctx.pinned_empty(n_samples, np.int16)
         ctx.synthesize_batch(elems, offs, vp, out=host_pcm, out_offsets=oo, fmt=g.I16)
-    barrier()
-    e2e_i16_value = world * n_samples * e2e_steps / max_over_ranks(time.perf_counter() - t0)
+        D.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.synthesize_batch(elems, offs, vp, out=host_pcm, out_offsets=oo, fmt=g.I16)
+        D.barrier()
+        e2e_i16 = {"value": total_samples * e2e_steps / D.max(time.perf_counter() - t0), "unit": UNIT,
+                   "d2h_bytes_per_step": int(n_samples * 2),
+                   "api": "grail_cuda_synthesize_batch_i16 (the reference's WAV sample format, pinned i16 out)"}
+    else:
+        checksum = float(out[: min(n_samples, 220476)].abs().sum().item())
 
     line = None
     if rank == 0:
-        # ---------------- roofline of the dominant kernel ----------------
-        probe = ctx.probe_fp32_peak()
-        peaks = measured_peaks()
-        achieved_tf = FLOPS_PER_SAMPLE_FORMANT * n_samples / (formant_ms * 1e-3) / 1e12
-        peak_tf = probe["ffma_flops"] / 1e12
-        hbm_bytes = 4 * n_samples * 2          # saw read + f32 samples written (algorithmic bytes of k_formant)
-        roofline = {
-            "kernel": "k_formant", "bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": achieved_tf / peak_tf, "traffic": NCU_TRAFFIC_BYTES,
-            "peak_source": "FFMA issue-rate probe measured live in this run (MEASURED_PEAKS.json has no fp32 figure)",
-            "flops_per_sample": FLOPS_PER_SAMPLE_FORMANT, "launch_ms": formant_ms,
-            "frac_active_formants": FLOPS_PER_SAMPLE_FORMANT_ACTIVE * n_samples / (formant_ms * 1e-3) / 1e12 / peak_tf,
-            "note": "achieved counts the reference's as-written flops (SURVEY 8d); the kernel executes fewer: 4 of the "
-                    "8 formants of the default voice are exactly zero and are skipped, and the 6 per-sample filter "
-                    "coefficients are interpolated between exact 16-sample end points, so frac exceeds 1; the honest "
-                    "efficiency figures are ncu's (profiles/r1_k_formant_ncu_full.txt): 9.1e8 warp instructions per "
-                    "launch, more than half of them packed FFMA2/FADD2/FMUL2 that hold the FP32 pipe for two cycles, "
-                    "issue slots 55 % busy, FMA-heavy pipe 46 % busy",
-            "mufu_peak_per_s": probe["mufu_ops"],
-            "hbm": {"achieved": hbm_bytes / (formant_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                    "frac": (hbm_bytes / (formant_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
-                    "peak_source": "MEASURED_PEAKS.json (measured)" if peaks.get("hbm_gbs") else "absent"},
-        }
+        roofline = roofline_block(ctx, n_samples, kern, ms / args.steps, args.config)
         # ---------------- CPU baseline on this box's host cores (bounded sample) ----------------
-        os.sched_setaffinity(0, all_cpus)
+        os.sched_setaffinity(0, D.all_cpus)
         cores = host_cores()
-        nb = max(cores, min(N_UTTS, 32 * cores))
-        cpu_baseline_run(max(1, nb // 8), cores)
+        if args.config == 3:
+            se, so, sv, cores_used, sample = elems, offs, vp, 1, "the whole 10-minute utterance once, one core"
+        else:
+            from grail_rs_b200 import sharding
+            n = len(offs) - 1
+            nb = min(n, max(cores, 32 * cores if args.config == 2 else 256 * cores))
+            se, so, sv = sharding.shard_batch(elems, offs, vp, np.arange(nb))
+            cores_used, sample = cores, f"the first {nb} of this rank's {n} utterances"
         n_cpu, dt_cpu = 0, 0.0
         while dt_cpu < 2.0:                      # bounded: ~10-30 core-seconds of CPU work
-            n_i, dt_i = cpu_baseline_run(nb, cores)
+            n_i, dt_i = cpu_run(se, so, sv, cores_used)
             n_cpu += n_i
             dt_cpu += dt_i
-        cpu = {"value": n_cpu / dt_cpu, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{nb} of the {N_UTTS} config-2 utterances, repeated to {n_cpu} samples ({dt_cpu:.2f} s wall), "
-                         "oracle -O3 strict f32, one utterance per task"}
+        cpu = {"value": n_cpu / dt_cpu, "unit": UNIT, "cores": cores_used, "kind": "port",
+               "sample": f"{sample}, repeated to {n_cpu} samples ({dt_cpu:.2f} s wall), oracle -O3 strict f32, one utterance per task"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"config2: {N_UTTS} utterances x {N_PHONEMES} phonemes (~5 s) per GPU, default voice, "
-                                   "44.1 kHz, jitter_seed = utterance index",
-                       "samples_per_step_per_gpu": n_samples, "l2": "inputs larger than L2 (2.7 GB touched per step)",
+            "config": {"workload": desc, "samples_per_step_rank0": n_samples, "samples_per_step_all_ranks": int(total_samples),
+                       "l2": f"inputs larger than L2 ({12 * n_samples / 1e9:.1f} GB touched per step)",
                        "parallelism": f"utterance-sharded x{world}, no data-path collective",
                        "pipeline": "consecutive steps overlap on two streams (plan option)" if args.pipeline else "off"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "api": "grail_cuda_synthesize_batch (host records in, pinned f32 out)",
-                    "cpus_bound_per_rank": numa},
-            "e2e_i16": {"value": e2e_i16_value, "unit": UNIT, "d2h_bytes_per_step": int(n_samples * 2),
-                        "api": "grail_cuda_synthesize_batch_i16 (the reference's WAV sample format, pinned i16 out)"},
+            "e2e": e2e if e2e is not None else {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                                                "skipped": f"output of {n_samples * 4 / 2**30:.1f} GiB per rank exceeds --e2e-max-gb"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "kernels_ms": kern, "rtf_per_gpu": value / world / SAMPLE_RATE, "checksum": checksum,
+            "kernels_ms": kern, "phase_stats": pstats, "rtf_per_gpu": value / world / float(vp[0]["sample_rate"]),
+            "checksum": checksum,
         }
+        if e2e_i16 is not None:
+            line["e2e_i16"] = e2e_i16
+        if cfg4 is not None:
+            line["config4"] = cfg4
     plan.close()
     ctx.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.close()
     if line is not None:
         print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours_config5(args):
+    """the config-2 shape at four sample rates: per rate the device-resident samples/s over all ranks, the end-to-end
+    figure, and (rank 0) the host CPU's samples/s on a bounded sample -- one JSON line with the table"""
+    D = Dist()
+    torch = D.torch
+    import grail_rs_b200 as g
+    from grail_rs_b200 import sharding
+    ctx = g.Context(D.local)
+    rows, tot_samples, tot_ms, launches = [], 0.0, 0.0, 0
+    clocks = None
+    for i, rate in enumerate(RATES_CONFIG5):
+        elems, offs, vp = workload_config2(D.rank, N_UTTS, rate)
+        ctx.set_option("pipeline", 1 if args.pipeline else 0)
+        plan = ctx.plan(elems, offs, vp)
+        ctx.set_option("pipeline", 0)
+        n = plan.total_samples
+        out = torch.empty(n, dtype=torch.float32, device="cuda")
+        sampler = ClockSampler(D.local) if (D.rank == 0 and i == 2) else None
+        ms, t0, t1 = timed_resident(D, ctx, plan, out.data_ptr(), args.steps, args.warmup, sampler)
+        if sampler is not None:
+            clocks = sampler.stop(t0, t1)
+        kern = kernel_split(ctx, plan, out.data_ptr(), 3)
+        launches += plan.timings()["n_launches"] * args.steps
+        total = D.sum(float(n))
+        row = {"sample_rate": rate, "samples_per_utterance": int(n // N_UTTS), "gpu_samples_per_s": total * args.steps / (ms * 1e-3),
+               "ms_per_step": ms / args.steps, "kernels_ms": kern, "rtf_per_gpu": total * args.steps / (ms * 1e-3) / D.world / rate}
+        if D.rank == 0:
+            os.sched_setaffinity(0, D.all_cpus)
+            cores = host_cores()
+            nb = min(N_UTTS, 32 * cores)
+            se, so, sv = sharding.shard_batch(elems, offs, vp, np.arange(nb))
+            n_cpu, dt_cpu = cpu_run(se, so, sv, cores)
+            row["cpu_samples_per_s"] = n_cpu / dt_cpu
+            row["cpu_cores"] = cores
+            row["cpu_sample"] = f"first {nb} utterances once"
+            row["gpu_over_cpu"] = row["gpu_samples_per_s"] / row["cpu_samples_per_s"]
+        rows.append(row)
+        tot_samples += total * args.steps
+        tot_ms += ms
+        plan.close()
+        del out
+    if D.rank == 0:
+        line = {"metric": METRIC, "value": tot_samples / (tot_ms * 1e-3), "unit": UNIT, "n_gpus": D.world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "config5: the config-2 shape (1 024 utterances x 10 phonemes per GPU, default voice rebuilt per "
+                                       "rate) at 16 / 22.05 / 44.1 / 48 kHz; a step = the four rates one after another",
+                           "l2": "inputs larger than L2", "rates": rows},
+                "e2e": {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                        "skipped": "see --config 2 for the end-to-end figure (same shape)"},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "cpu_baseline": {"value": float(np.mean([r["cpu_samples_per_s"] for r in rows])), "unit": UNIT,
+                                 "cores": rows[0]["cpu_cores"], "kind": "port", "sample": "per rate: " + rows[0]["cpu_sample"]}}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    D.close()
     return 0
 
 
@@ -362,6 +618,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json workload (2 = headline)")
+    ap.add_argument("--gather", type=int, default=1, help="config 4, N > 1: gather the outputs into batch order over NCCL")
+    ap.add_argument("--parity-utts", type=int, default=64, help="config 4: utterances per rank checked against the oracle")
+    ap.add_argument("--e2e-max-gb", type=float, default=4.0, help="skip the end-to-end leg when a rank's f32 output is larger")
     ap.add_argument("--pipeline", type=int, default=1, help="overlap consecutive steps of the resident plan (0 = launch in order)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -79,7 +79,7 @@ struct PlanDev {
     const ItemDev*      items;
     JitSchedDev*        jscheds;
     JitRec*             jrecs;
-    float*              F;         // linear, per utterance at f_off
+    float*              F;         // F_t: linear, per utterance at f_off -- or, when f_tiled, in the saw's tiled layout
     float*              saw;       // tiled: [group][j/8][lane][8]
     float*              phase_dbg; // optional linear carrier phase tap (same indexing as F), may be null
     uint32_t*           fflags;    // one word per 128 F_t entries: nonzero if any is negative or NaN
@@ -93,6 +93,8 @@ struct PlanDev {
     uint32_t*           pstats;    // 64 words: see PSTAT_*
     uint32_t            phase_chunk; // PC, multiple of 256 (0: chunk-parallel path off)
     uint32_t            n_pchunks;
+    uint32_t            pc_per_item; // K = ceil(chunk_len / phase_chunk): phase chunks per work item
+    uint32_t            f_tiled;   // F is tiled like the saw (plans with the chunk-parallel phase)
     uint32_t*           err;       // device error word
     uint32_t n_utts, n_items, n_groups, n_jscheds;
     uint32_t chunk_len;            // CL, multiple of 256
@@ -308,7 +310,10 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
     s_next = lcg_step(s_next);
     float nxt = lcg_float(s_next);
 
-    float* dst = P.F + U.f_off + ns;
+    // linear: one row per utterance; tiled: the saw's layout, 8-sample block b of this run 256 floats further each
+    const bool tiled = P.f_tiled != 0u;
+    float* dst = tiled ? P.F + saw_index(item, off, P.chunk_len) : P.F + U.f_off + ns;
+    const uint32_t bstep = tiled ? 256u : 8u;   // distance between consecutive 8-sample blocks
     double fsum = 0.0;  // exact sum of this run's F_t (every term is a multiple of 2^-40 or so): k_phase_guess's raw material
     bool odd = false;   // any increment that is negative or NaN: k_phase then takes its fully general path
     // one sample of the scalar frequency path, strict ops in the reference's order
@@ -340,14 +345,14 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
                 time = ssub(time, dt);                                                     // :861
                 jph = sadd(jph, jinc);                                                     // :242
             }
-            float4* d4 = reinterpret_cast<float4*>(dst + k0);
+            float4* d4 = reinterpret_cast<float4*>(dst + (k0 >> 3) * bstep);
             d4[0] = make_float4(buf[0], buf[1], buf[2], buf[3]);
             d4[1] = make_float4(buf[4], buf[5], buf[6], buf[7]);
         } else {
             const uint32_t kend = min(k0 + 8, count);
 #pragma unroll 1
             for (uint32_t k = k0; k < kend; ++k) {
-                dst[k] = freq_sample();
+                dst[(k >> 3) * bstep + (k & 7u)] = freq_sample();
                 time = ssub(time, dt);                                                     // :861
                 if (time < 0.0f) {                                                         // :864
                     ++p;
@@ -372,7 +377,10 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
         // the lane that wrote the utterance's last sample rounds the row up: k_phase_pair copies F_t in groups of 8
         // and the flag words in pairs, so nothing it touches is left unwritten (the values themselves are unused)
         const uint32_t n = U.n_samples;
-        for (uint32_t i = n; i < ((n + 7u) & ~7u); ++i) P.F[U.f_off + i] = 0.0f;
+        for (uint32_t i = n; i < ((n + 7u) & ~7u); ++i) {
+            const uint32_t k = i - ns;             // same 8-sample block as the last sample
+            dst[(k >> 3) * bstep + (k & 7u)] = 0.0f;
+        }
         if ((((n - 1u) >> 7) & 1u) == 0u) P.fflags[((U.f_off + n - 1u) >> 7) + 1u] = 0u;
     }
 }
@@ -574,6 +582,8 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
     if (is_chain) {
         // ---------------- chain warp ----------------
         const float* src = P.F + U.f_off;
+        const bool tiled = P.f_tiled != 0u;                  // (plans of the chunk-parallel phase: this kernel is their fallback)
+        const uint32_t CLt = P.chunk_len;
         const uint32_t* flags = P.fflags + (U.f_off >> 7);   // f_off is a multiple of 256: 8-byte aligned pairs
         const uint32_t npad = (n + 7u) & ~7u;
         const unsigned sF_a = (unsigned)__cvta_generic_to_shared(&sF[slot][0][0]);
@@ -584,8 +594,13 @@ __global__ void __launch_bounds__(PH_UTTS * 64) k_phase_pair(PlanDev P)
                 const uint32_t off = tile * PH_TILE + lane * 8;
                 const unsigned dst = sF_a + ((tile % PH_STAGES) * PH_TILE + lane * 8) * 4;
                 if (off < npad) {
-                    cp_async16(dst, src + off);
-                    cp_async16(dst + 16, src + off + 4);
+                    const float* g8 = src + off;
+                    if (tiled) {
+                        const uint32_t ci = off / CLt;
+                        g8 = P.F + saw_index(U.item_first + ci * U.item_stride, off - ci * CLt, CLt);
+                    }
+                    cp_async16(dst, g8);
+                    cp_async16(dst + 16, g8 + 4);
                 }
                 // the tile's two sign-flag words ride the same ring (the flag array is padded past the end)
                 if (lane == 0) cp_async8(sG_a + (tile % PH_STAGES) * 8, flags + 2 * tile);
@@ -1279,7 +1294,12 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
 #pragma unroll
     for (int j = 0; j < FPT; ++j) {
         uint32_t wl = 0;
-        if (on && it.n0 > 0 && L[j].fi >= 0) wl = warmup_len(ue, segs, n_elems, it.n0, L[j].fi, dff, P.warmup_nepers);
+        if (on && it.n0 > 0 && L[j].fi >= 0) {
+            wl = warmup_len(ue, segs, n_elems, it.n0, L[j].fi, dff, P.warmup_nepers);
+            // a formant that rings longer than the utterance has lasted so far: this lane recomputes it from sample 0
+            // (exact, but the time parallelism is gone for it) -- counted, so that the cliff shows in the plan's stats
+            if (wl >= it.n0 && P.pstats) atomicAdd(P.pstats + 8, 1u);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) wl = max(wl, __shfl_xor_sync(0xffffffffu, wl, o));
         wslot[j] = (wl + 15u) & ~15u;             // whole 16-sample interpolation blocks
@@ -1343,7 +1363,10 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
             L[j].xff = 0.f;
             fold_jitter(j, c0, lcg_float(L[j].s_ff), c1, lcg_float(L[j].s_amp));
             L[j].xff = 0.f; L[j].ff0 = dff * c0;      // base added by load_segment below
-            if (it.n0 == 0 && U.has_init) {           // a continued stream: the Synthesize filter states carry over
+            // A continued stream: the Synthesize filter states carry over.  They apply to every slot whose run starts at
+            // the window's sample 0 -- the first chunk, and any later chunk whose warm-up reaches back to sample 0 (there
+            // a start from rest would ignore the carried state; its error decays only with the warm-up actually available).
+            if (U.has_init && wslot[j] >= it.n0) {
                 const float* st0 = P.utt_init + (size_t)it.utt * 32;
                 L[j].a = st0[L[j].fi]; L[j].b = st0[8 + L[j].fi]; L[j].c = st0[16 + L[j].fi];
             }
@@ -1500,7 +1523,8 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
         }
         if (FPT == 2 && r == r_join && r_join != -(int)wmax) {
             // the second slot starts here, from rest (whatever the exact / hand-over rows before may have left in it)
-            if (act) { L[FPT - 1].a = 0.f; L[FPT - 1].b = 0.f; L[FPT - 1].c = 0.f; }
+            // (... unless it starts at the window's sample 0 of a continued stream: it then holds the carried state)
+            if (act && !(U.has_init && wslot[FPT - 1] >= it.n0)) { L[FPT - 1].a = 0.f; L[FPT - 1].b = 0.f; L[FPT - 1].c = 0.f; }
             c_valid = false;
         }
         if (act) {
@@ -1719,6 +1743,44 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
 #pragma unroll
         for (int j = 0; j < FPT; ++j)
             if (L[j].fi >= 0) { fin[L[j].fi] = L[j].a; fin[8 + L[j].fi] = L[j].b; fin[16 + L[j].fi] = L[j].c; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Output gather helper (multi-GPU): segment i of `src` goes to its place in `dst`.  One CTA per (segment, tile of
+// SEG_TILE elements); 16-byte copies where source and destination are equally aligned, element copies otherwise.
+// ------------------------------------------------------------------------------------------------
+struct SegCopy { unsigned long long dst, src, len; };   // byte offsets / byte length
+constexpr unsigned long long SEG_TILE_BYTES = 1ull << 16;
+__global__ void __launch_bounds__(256) k_copy_segments(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src,
+                                                       const SegCopy* __restrict__ segs, const uint32_t* __restrict__ tile_seg,
+                                                       const uint32_t* __restrict__ tile_idx, uint32_t elem_bytes)
+{
+    const SegCopy sg = segs[tile_seg[blockIdx.x]];
+    const unsigned long long b0 = (unsigned long long)tile_idx[blockIdx.x] * SEG_TILE_BYTES;
+    const unsigned long long b1 = min(b0 + SEG_TILE_BYTES, sg.len);
+    unsigned char* d = dst + sg.dst;
+    const unsigned char* s = src + sg.src;
+    if ((((uintptr_t)(d + b0)) & 15u) == (((uintptr_t)(s + b0)) & 15u)) {
+        // head up to the next 16-byte boundary, body in 16-byte words, tail: element by element
+        unsigned long long head = (16u - (((uintptr_t)(d + b0)) & 15u)) & 15u;
+        head = min(head, b1 - b0);
+        for (unsigned long long i = b0 + (unsigned long long)threadIdx.x * elem_bytes; i < b0 + head; i += 256ull * elem_bytes)
+            for (uint32_t k = 0; k < elem_bytes; ++k) d[i + k] = s[i + k];
+        const unsigned long long body0 = b0 + head, nvec = (b1 - body0) >> 4;
+        const uint4* sv = reinterpret_cast<const uint4*>(s + body0);
+        uint4* dv = reinterpret_cast<uint4*>(d + body0);
+        for (unsigned long long i = threadIdx.x; i < nvec; i += 256) dv[i] = __ldg(sv + i);
+        for (unsigned long long i = body0 + (nvec << 4) + (unsigned long long)threadIdx.x * elem_bytes; i < b1; i += 256ull * elem_bytes)
+            for (uint32_t k = 0; k < elem_bytes; ++k) d[i + k] = s[i + k];
+    } else if (elem_bytes == 4) {
+        const uint32_t* sv = reinterpret_cast<const uint32_t*>(s + b0);
+        uint32_t* dv = reinterpret_cast<uint32_t*>(d + b0);
+        for (unsigned long long i = threadIdx.x; i < ((b1 - b0) >> 2); i += 256) dv[i] = __ldg(sv + i);
+    } else {
+        const uint16_t* sv = reinterpret_cast<const uint16_t*>(s + b0);
+        uint16_t* dv = reinterpret_cast<uint16_t*>(d + b0);
+        for (unsigned long long i = threadIdx.x; i < ((b1 - b0) >> 1); i += 256) dv[i] = sv[i];
     }
 }
 

@@ -8,7 +8,7 @@
 //     later grids are no coarser than 2^-23 and no finer grid's rounding can tell them apart, round-half-even ties
 //     included (an odd multiple flips the parity that decides a tie on a wrap step) -- unless one of the two reaches
 //     a binade boundary or 1.0 a step earlier than the other, which needs the boundary to fall inside that small gap.
-// So an utterance is cut into chunks of PC samples, one lane each, and
+// So an utterance is cut into phase chunks of at most PC samples, one lane each, and
 //   k_phase_guess   start-phase guesses from the exact sums of F_t (k_frequency emits one sum per 256 samples); they
 //                   ignore the accumulator's rounding and are off by tens of 2^-23 units after a few seconds;
 //   k_phase_a       walks every chunk literally from its guess to its first wrap (the anchor), then, as two
@@ -25,6 +25,17 @@
 // An utterance that is still unproven after the last round keeps status bit 0 clear and k_phase_pair runs the
 // serial chain for it.  Nothing here assumes anything about F_t: negative, NaN or tiny increments only make the
 // guesses worse, the proof decides.
+//
+// Memory: F_t lives in the SAME tiled layout as the saw, [group of 32 work items][j / 8][lane][8] (saw_index), and a
+// warp of the walks is the same sub-range of 32 work items of one k_formant group: lane l reads 32 bytes of item l per
+// 8-sample block, the warp 1 KB of consecutive addresses, and round B stores the saw to the very same offsets.  Both
+// rounds are plain streaming kernels bound by HBM (round A reads F_t about 1.2 times, round B reads it once and
+// writes the saw once); the loads run four blocks ahead of the arithmetic in registers.
+// (First version, kept in profiles/r2_phase_strided_launches.csv: linear F_t, one lane per CONSECUTIVE chunk of an
+//  utterance, i.e. 32 lanes reading 32 places 8 KB apart -- per-lane 128-byte TMA bulk copies (cp.async.bulk +
+//  mbarrier complete_tx) into private shared-memory rows as well as LDG.256 / 16-byte cp.async all ended at 0.84 ms
+//  for round A and 0.85 ms for round B at config 2, bound by one L1 tag look-up / one TMA request per 32-byte
+//  sector: the access pattern, not the copy engine, was the problem.)
 #pragma once
 
 namespace grail {
@@ -49,15 +60,10 @@ enum { PSTAT_WALKS = 0,       // chunks walked by k_phase_b, all rounds
        PSTAT_UNPROVEN = 1,    // utterances left to the serial chain
        PSTAT_ROUNDS = 2,      // last repair round that still found a mismatch (0: the first walk proved everything)
        PSTAT_MISMATCH = 3,    // chunk boundaries that failed the proof, all rounds
+       PSTAT_WARMUP_FROM_ZERO = 8,   // k_formant: (chunk, formant) pairs whose filter warm-up reached back to sample 0
        PSTAT_PENDING = 16 };  // + r: dirty chunks waiting for round r's k_phase_b
 
 constexpr int PH_MAX_ROUNDS = 14;
-#ifndef PH_LOOKAHEAD
-#define PH_LOOKAHEAD 2     // 32-sample rows of F_t per lane in shared memory (18 KB each per CTA of 128 lanes)
-#endif
-#ifndef PH_OCC
-#define PH_OCC 6           // CTAs of 128 lanes per SM the walks are compiled for
-#endif
 constexpr float PH_U23 = 1.1920928955078125e-07f;   // 2^-23
 
 __device__ __forceinline__ float* pcf(const PlanDev& P, int field) { return P.pchunks + (size_t)field * P.pc_stride; }
@@ -95,15 +101,108 @@ __device__ __forceinline__ double centered_diff(float x, float y)
     return d;
 }
 
-// utterance that owns global phase chunk g
-__device__ __forceinline__ uint32_t pchunk_utt(const UttDev* utts, uint32_t n_utts, uint32_t g)
+// ------------------------------------------------------------------------------------------------
+// Phase chunks.  Work item (time chunk of k_formant, CL samples) i of an utterance is cut into K = ceil(CL / PC)
+// phase chunks of PC samples (the last one of an item shorter when PC does not divide CL); an utterance's chunks are
+// numbered in time order, chunk c = item * K + q, and stored at pc_first + c.  A warp of the walks is sub-range q of
+// the 32 items of one k_formant group.
+// ------------------------------------------------------------------------------------------------
+struct PChunkLane {
+    uint32_t u;          // utterance
+    uint32_t g, c, C;    // global chunk index, index within the utterance, chunks of the utterance
+    uint32_t n0, n1;     // samples [n0, n1) of the utterance
+    uint32_t nn1;        // end of the NEXT chunk of the utterance (n1 when there is none)
+    bool     valid;
+};
+__device__ __forceinline__ PChunkLane pchunk_of_lane(const PlanDev& P)
 {
-    uint32_t lo = 0, hi = n_utts;    // last utterance with pc_first <= g (utterances without samples share their successor's pc_first)
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (utts[mid].pc_first <= g) lo = mid; else hi = mid;
+    PChunkLane X;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    const uint32_t K = P.pc_per_item, PC = P.phase_chunk, CL = P.chunk_len;
+    const uint32_t group = warp / K, q = warp - group * K;
+    const uint32_t item = group * 32u + lane;
+    X.valid = false;
+    X.u = 0; X.g = X.c = X.C = X.n0 = X.n1 = X.nn1 = 0;
+    if (item >= P.n_items) return X;
+    const ItemDev it = P.items[item];
+    const uint32_t s0 = q * PC;
+    if (s0 >= it.len) return X;
+    const UttDev& U = P.utts[it.utt];
+    X.valid = true;
+    X.u = it.utt;
+    X.C = U.pc_count;
+    X.c = (it.n0 / CL) * K + q;
+    X.g = U.pc_first + X.c;
+    X.n0 = it.n0 + s0;
+    X.n1 = it.n0 + min(min(s0 + PC, CL), it.len);
+    const uint32_t n = U.n_samples;
+    uint32_t len2 = 0;
+    if (X.n1 < n) {
+        const uint32_t j1 = X.n1 - (X.n1 / CL) * CL;              // position of the next chunk inside its item
+        len2 = min(min(PC, CL - j1), n - X.n1);
     }
-    return lo;
+    X.nn1 = X.n1 + len2;
+    return X;
+}
+
+// Cursor over an utterance's F_t / saw in the tiled layout, one 8-sample block at a time.
+struct TileCursor {
+    size_t   off;        // float offset of the current block (of this utterance's sample `t`)
+    uint32_t j;          // position inside the item, multiple of 8
+    uint32_t item;
+    uint32_t CL, stride;
+    __device__ __forceinline__ void seek(const UttDev& U, uint32_t t, uint32_t cl)
+    {
+        CL = cl; stride = U.item_stride;
+        const uint32_t ci = t / cl;
+        item = U.item_first + ci * stride;
+        j = t - ci * cl;
+        off = saw_index(item, j, cl);
+    }
+    __device__ __forceinline__ void next()
+    {
+        j += 8u;
+        if (j >= CL) { j = 0u; item += stride; off = saw_index(item, 0u, CL); }
+        else off += 256u;
+    }
+};
+
+// fn(blk, off, f) for every 8-sample block of [t0, t1) (both multiples of 8) in order; `off` is the block's offset in
+// the tiled arrays; fn returns false to stop early.  Loads run four blocks ahead (32 registers).
+template <class Fn>
+__device__ __forceinline__ void walk_blocks(const float* __restrict__ F, const UttDev& U, uint32_t CL, uint32_t t0, uint32_t t1,
+                                            Fn&& fn)
+{
+    if (t0 >= t1) return;
+    TileCursor ld, cur;
+    ld.seek(U, t0, CL);
+    cur = ld;
+    uint32_t tl = t0;
+    float r0[8], r1[8], r2[8], r3[8];
+#define PH_FETCH(R)                                   \
+    do {                                              \
+        if (tl < t1) { ldg256(F + ld.off, R); ld.next(); tl += 8u; } \
+    } while (0)
+    PH_FETCH(r0); PH_FETCH(r1); PH_FETCH(r2); PH_FETCH(r3);
+    uint32_t blk = t0;
+    bool go = true;
+#define PH_USE(R)                                     \
+    do {                                              \
+        if (go && blk < t1) {                         \
+            float f_[8];                              \
+            _Pragma("unroll") for (int k_ = 0; k_ < 8; ++k_) f_[k_] = R[k_]; \
+            PH_FETCH(R);                              \
+            go = fn(blk, cur.off, f_);                \
+            cur.next();                               \
+            blk += 8u;                                \
+        }                                             \
+    } while (0)
+#pragma unroll 1
+    while (go && blk < t1) {
+        PH_USE(r0); PH_USE(r1); PH_USE(r2); PH_USE(r3);
+    }
+#undef PH_FETCH
+#undef PH_USE
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -116,21 +215,23 @@ __global__ void __launch_bounds__(128) k_phase_guess(PlanDev P)
     if (u >= P.n_utts) return;
     const UttDev& U = P.utts[u];
     if (lane == 0) P.utt_status[u] = 0u;
-    const uint32_t C = U.pc_count, PC = P.phase_chunk;
+    const uint32_t C = U.pc_count, PC = P.phase_chunk, K = P.pc_per_item, CL = P.chunk_len;
     if (C == 0) return;
     float* start = pcf(P, PCF_START) + U.pc_first;
     int32_t* flags = pci(P, PCF_FLAGS) + U.pc_first;
     const double* bs = P.bsum + (U.f_off >> 8);
-    const uint32_t runs = (U.n_samples + 255u) >> 8, rpc = PC >> 8;
-    double carry = (double)U.init_phase;
+    const uint32_t n = U.n_samples;
     auto chunk_sum = [&](uint32_t c) -> double {
         double s = 0.0;
         if (c < C) {
-            const uint32_t r0 = c * rpc, r1 = min(r0 + rpc, runs);
+            const uint32_t ci = c / K, q = c - ci * K;
+            const uint32_t s0 = ci * CL + q * PC, s1 = min(ci * CL + min(q * PC + PC, CL), n);   // multiples of 256 (but the end)
+            const uint32_t r0 = s0 >> 8, r1 = (s1 + 255u) >> 8;
             for (uint32_t r = r0; r < r1; ++r) s = frac_d(s + bs[r]);
         }
         return s;
     };
+    double carry = (double)U.init_phase;
     double s_next = chunk_sum(lane);
     for (uint32_t c0 = 0; c0 < C; c0 += 32) {
         const uint32_t c = c0 + lane;
@@ -152,93 +253,6 @@ __global__ void __launch_bounds__(128) k_phase_guess(PlanDev P)
         }
         carry = frac_d(carry + __shfl_sync(0xffffffffu, incl, 31));
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// F_t reader of the walks.  A lane streams its own chunk -- 32 lanes of a warp read 32 places 4-8 KB apart, the
-// worst case for the L1 (one tag look-up per 32-byte sector: measured, the walks were bound by exactly that with
-// LDG.256 and with 16-byte cp.async alike).  So the stream goes through the TMA instead: every lane moves 128-byte
-// ROWS (32 samples) of its chunk into a private slice of shared memory with cp.async.bulk (UBLKCP), completion on a
-// private mbarrier (complete_tx), PH_ROWS rows per lane, the next row in flight while the current one is stepped.
-// Slice, barrier and data are touched by the issuing lane only: no warp- or CTA-level synchronisation, and lanes
-// may diverge freely (round A's lanes leave their loops at different samples).  Rows are 144 bytes apart:
-// conflict-free 128-bit reads.  fn(blk, f) is called for every 8-sample block of [b0, b1) in order and returns false
-// to stop early.  Rows are copied whole; the F_t buffer is padded so that a row may reach past its utterance.
-// ------------------------------------------------------------------------------------------------
-constexpr uint32_t PH_ROWS = PH_LOOKAHEAD;       // rows per lane (power of two)
-constexpr uint32_t PH_LANES = 128;
-constexpr uint32_t PH_ROW_STRIDE = 144;          // 128 bytes of samples + 16 of padding
-constexpr uint32_t PH_RING_BYTES = PH_ROWS * PH_LANES * PH_ROW_STRIDE;
-
-struct PhRing {
-    unsigned data;        // shared-window address of this lane's row 0 (row r at + r * PH_LANES * PH_ROW_STRIDE)
-    unsigned bar;         // ... of its mbarrier 0 (8 bytes each)
-    uint32_t parity;      // bit r: parity of the phase row r's next completion will end
-};
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned a, unsigned bytes)
-{
-    asm volatile("{ .reg .b64 t; mbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1; }" ::"r"(a), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ PhRing ph_ring_init(unsigned char* smem, uint64_t* bars)
-{
-    PhRing R;
-    R.data = (unsigned)__cvta_generic_to_shared(smem) + threadIdx.x * PH_ROW_STRIDE;
-    R.bar = (unsigned)__cvta_generic_to_shared(bars + threadIdx.x * PH_ROWS);
-    R.parity = 0u;
-#pragma unroll
-    for (uint32_t r = 0; r < PH_ROWS; ++r) mbar_init(bars + threadIdx.x * PH_ROWS + r, 1);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the barriers are visible to the TMA
-    return R;
-}
-
-template <class Fn>
-__device__ __forceinline__ void stream_blocks(PhRing& R, const float* __restrict__ F, uint32_t b0, uint32_t b1, Fn&& fn)
-{
-    if (b0 >= b1) return;
-    const uint32_t r0 = b0 & ~31u;
-    uint32_t inflight = 0u;                        // bit r: row slot r has a copy in flight
-    auto issue = [&](uint32_t row) {
-        if (row < b1) {
-            const uint32_t r = (row >> 5) & (PH_ROWS - 1u);
-            mbar_arrive_expect_tx(R.bar + r * 8u, 128u);
-            bulk_g2s(R.data + r * (PH_LANES * PH_ROW_STRIDE), F + row, 128u, R.bar + r * 8u);
-            inflight |= 1u << r;
-        }
-    };
-    auto land = [&](uint32_t r) {
-        mbar_wait(R.bar + r * 8u, (R.parity >> r) & 1u);
-        R.parity ^= 1u << r;
-        inflight &= ~(1u << r);
-    };
-#pragma unroll 1
-    for (uint32_t i = 0; i + 1u < PH_ROWS; ++i) issue(r0 + 32u * i);
-    bool go = true;
-#pragma unroll 1
-    for (uint32_t row = r0; row < b1 && go; row += 32u) {
-        issue(row + 32u * (PH_ROWS - 1u));
-        const uint32_t r = (row >> 5) & (PH_ROWS - 1u);
-        land(r);
-        const unsigned src = R.data + r * (PH_LANES * PH_ROW_STRIDE);
-#pragma unroll 1
-        for (uint32_t i = 0; i < 4u && go; ++i) {
-            const uint32_t blk = row + 8u * i;
-            if (blk >= b0 && blk < b1) {
-                const float4 fa = lds128(src + i * 32u), fb = lds128(src + i * 32u + 16u);
-                const float f[8] = { fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w };
-                go = fn(blk, f);
-            }
-        }
-    }
-    // rows still in flight (an early stop) must land before the slots and their barriers are used again
-#pragma unroll
-    for (uint32_t r = 0; r < PH_ROWS; ++r)
-        if (inflight & (1u << r)) land(r);
 }
 
 // 8 literal steps; returns the number of wraps as a float sum.  (Blocks that reach past the utterance's end read the
@@ -272,73 +286,55 @@ __device__ __forceinline__ int first_wrap8(float p, const float (&f)[8], float* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// round A: one lane per chunk
+// round A: one lane per chunk, one pass over [n0, first wrap of both trajectories inside the next chunk], the 32
+// lanes of a warp in step over the same blocks of their 32 items
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, PH_OCC) k_phase_a(PlanDev P)
+__global__ void __launch_bounds__(128) k_phase_a(PlanDev P)
 {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= P.n_pchunks) return;
-    const uint32_t u = pchunk_utt(P.utts, P.n_utts, g);
-    const UttDev& U = P.utts[u];
-    const uint32_t c = g - U.pc_first, C = U.pc_count;
-    const bool last = c + 1 >= C;                 // the last chunk hands no phase on, but the scan needs its anchor
-    if (last && c == 0) return;
-    const uint32_t PC = P.phase_chunk, n = U.n_samples;
-    const uint32_t n0 = c * PC, n1 = min(n0 + PC, n), nn1 = min(n1 + PC, n);
-    const float* F = P.F + U.f_off;
-
-    __shared__ __align__(16) unsigned char ring_mem[PH_RING_BYTES];
-    __shared__ __align__(8) uint64_t ring_bar[PH_LANES * PH_ROWS];
-    PhRing ring = ph_ring_init(ring_mem, ring_bar);
+    const PChunkLane X = pchunk_of_lane(P);
+    if (!X.valid) return;
+    const bool last = X.c + 1 >= X.C;             // the last chunk hands no phase on, but the scan needs its anchor
+    if (last && X.c == 0) return;
+    const UttDev& U = P.utts[X.u];
+    const uint32_t g = X.g, n1 = X.n1;
     float p0 = pcf(P, PCF_START)[g], p1 = p0;
-    int32_t a = -1;
-    float R = 0.0f;
-    uint32_t t2 = n0;                             // first sample of the two-trajectory walk
-    if (c != 0) {
-        // stage 1: from the guess to the first wrap inside the chunk
-        float p = p0;
-        stream_blocks(ring, F, n0, (n1 + 7u) & ~7u, [&](uint32_t blk, const float (&f)[8]) -> bool {
-            const float pb = p;
-            if (steps8(p, f) != 0.0f) {
-                a = (int32_t)blk + first_wrap8(pb, f, &R);
-                return false;
-            }
-            return true;
-        });
-        if (last) { pci(P, PCF_A)[g] = a; pcf(P, PCF_R)[g] = R; return; }
-        if (a >= 0) {
-            t2 = (uint32_t)a + 1u;
-            p0 = R;
-            p1 = sadd(R, PH_U23);                 // exact: R is a small multiple of 2^-23
-        } else {
-            t2 = n1;                              // no wrap in the whole chunk: one trajectory, the guess's own
-            p0 = p1 = p;
-        }
-    }
-    // stage 2: both trajectories to the chunk's end (n1 is a multiple of 8 here: the chunk has a successor)
-    if (t2 < n1) {
-        stream_blocks(ring, F, t2 & ~7u, n1, [&](uint32_t blk, const float (&f)[8]) -> bool {
-            if (blk >= t2) {
+    int32_t a = -1, a20 = -1, a21 = -1;
+    float R = 0.0f, R20 = 0.0f, R21 = 0.0f, E0 = p0, E1 = p0;
+    bool two = X.c == 0;                          // chunk 0 starts exact: one trajectory, no anchor needed
+    // n1 is a multiple of 8 when the chunk has a successor (chunk ends are multiples of 256 but the utterance's)
+    const uint32_t t_end = last ? ((n1 + 7u) & ~7u) : ((X.nn1 + 7u) & ~7u);
+    walk_blocks(P.F, U, P.chunk_len, X.n0, t_end, [&](uint32_t blk, size_t, const float (&f)[8]) -> bool {
+        if (blk < n1) {
+            if (two) {
                 steps8(p0, f);
                 steps8(p1, f);
-            } else {                              // the rest of the anchor's block
+            } else {
+                // stage 1: from the guess towards the first wrap inside the chunk
+                const float pb = p0;
+                if (steps8(p0, f) != 0.0f) {
+                    const int k = first_wrap8(pb, f, &R);
+                    a = (int32_t)blk + k;
+                    if (last) return false;
+                    p0 = R;
+                    p1 = sadd(R, PH_U23);         // exact: R is a small multiple of 2^-23
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    if (blk + k >= t2) {
-                        float g0, g1;
-                        p0 = phase_step(p0, f[k], g0);
-                        p1 = phase_step(p1, f[k], g1);
+                    for (int i = 1; i < 8; ++i) {  // the rest of the anchor's block, both trajectories
+                        if (i > k) {
+                            float g0, g1;
+                            p0 = phase_step(p0, f[i], g0);
+                            p1 = phase_step(p1, f[i], g1);
+                        }
                     }
+                    two = true;
                 }
             }
             return true;
-        });
-    }
-    const float E0 = p0, E1 = p1;
-    // stage 3: on to the first wrap inside the next chunk
-    int32_t a20 = -1, a21 = -1;
-    float R20 = 0.0f, R21 = 0.0f;
-    stream_blocks(ring, F, n1, (nn1 + 7u) & ~7u, [&](uint32_t blk, const float (&f)[8]) -> bool {
+        }
+        // stage 3: on to the first wrap of each trajectory inside the next chunk
+        if (blk == n1) {
+            if (!two) p1 = p0;                    // no wrap in the whole chunk: one trajectory, the guess's own
+            E0 = p0; E1 = p1;
+        }
         const float b0 = p0, b1 = p1;
         const float w0 = steps8(p0, f), w1 = steps8(p1, f);
         if (w0 != 0.0f && a20 < 0) a20 = (int32_t)blk + first_wrap8(b0, f, &R20);
@@ -346,6 +342,7 @@ __global__ void __launch_bounds__(128, PH_OCC) k_phase_a(PlanDev P)
         return a20 < 0 || a21 < 0;
     });
     pci(P, PCF_A)[g] = a; pcf(P, PCF_R)[g] = R;
+    if (last) return;
     pcf(P, PCF_E0)[g] = E0; pcf(P, PCF_E1)[g] = E1;
     pci(P, PCF_A20)[g] = a20; pci(P, PCF_A21)[g] = a21;
     pcf(P, PCF_R20)[g] = R20; pcf(P, PCF_R21)[g] = R21;
@@ -490,22 +487,17 @@ __device__ __forceinline__ uint32_t wrap_tie1(float p, float f)
     return 0u;
 }
 // Blocks that hold a polyBLEP edge sample (the sample before and the sample after a carrier wrap: 2 in ~370 at
-// 120 Hz) are only NOTED by the walk -- block index and the phase at its start -- and redone afterwards, one block
-// at a time: the divisions of the polyBLEP and the tie test then cost a lane what its own wraps cost, instead of
+// 120 Hz) are only NOTED by the walk -- tiled offset and the phase at the block's start -- and redone afterwards, one
+// block at a time: the divisions of the polyBLEP and the tie test then cost a lane what its own wraps cost, instead of
 // every lane of the warp paying for every other lane's wraps inside the hot loop.
 constexpr int PH_EDGE_BUF = 24;
 
-struct EdgeCtx {
-    const float* F;
-    float* saw;
-    float* dbg;
-    uint32_t item_first, item_stride, CL;
-};
-__device__ __noinline__ uint32_t phase_b_redo_block(const EdgeCtx X, uint32_t blk, float p, uint32_t want_tie)
+__device__ __noinline__ uint32_t phase_b_redo_block(const float* __restrict__ F, float* __restrict__ saw, size_t off, float p,
+                                                    uint32_t want_tie)
 {
     float f[8];
-    ldg256(X.F + blk, f);
-    float* dst = X.saw + saw_index(X.item_first + (blk / X.CL) * X.item_stride, blk % X.CL, X.CL);
+    ldg256(F + off, f);
+    float* dst = saw + off;
     uint32_t tie = 0u;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -518,41 +510,33 @@ __device__ __noinline__ uint32_t phase_b_redo_block(const EdgeCtx X, uint32_t bl
     return tie;
 }
 
-__global__ void __launch_bounds__(128, PH_OCC) k_phase_b(PlanDev P, uint32_t round)
+__global__ void __launch_bounds__(128) k_phase_b(PlanDev P, uint32_t round)
 {
     if (round != 0 && P.pstats[PSTAT_PENDING + round] == 0u) return;   // nothing is dirty: the whole grid leaves
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= P.n_pchunks) return;
+    const PChunkLane X = pchunk_of_lane(P);
+    if (!X.valid) return;
+    const uint32_t g = X.g;
     if (!((uint32_t)pci(P, PCF_FLAGS)[g] & PCH_DIRTY)) return;
-    const uint32_t u = pchunk_utt(P.utts, P.n_utts, g);
-    const UttDev& U = P.utts[u];
-    const uint32_t c = g - U.pc_first;
-    const uint32_t PC = P.phase_chunk, n = U.n_samples, CL = P.chunk_len;
-    const uint32_t n0 = c * PC, n1 = min(n0 + PC, n);
-    const float* F = P.F + U.f_off;
+    const UttDev& U = P.utts[X.u];
+    const uint32_t CL = P.chunk_len, n0 = X.n0, n1 = X.n1;
+    const float* F = P.F;
     float* dbg = P.phase_dbg ? P.phase_dbg + U.f_off : nullptr;
-    const uint32_t item_stride = U.item_stride;
-    uint32_t dst_item = U.item_first + (n0 / CL) * item_stride, dst_j = n0 % CL;
-    EdgeCtx X;
-    X.F = F; X.saw = P.saw; X.dbg = dbg; X.item_first = U.item_first; X.item_stride = item_stride; X.CL = CL;
     float p = pcf(P, PCF_START)[g];
     uint32_t tie = 0u;
-    uint32_t eb_blk[PH_EDGE_BUF];
+    // note pad: the tiled offsets fit 32 bits in units of 8 floats (2^35 floats)
+    uint32_t eb_off[PH_EDGE_BUF];
     float eb_p[PH_EDGE_BUF];
     int eb_n = 0;
     auto flush = [&]() {
 #pragma unroll 1
         for (int i = 0; i < eb_n; ++i) {
-            const uint32_t t = phase_b_redo_block(X, eb_blk[i], eb_p[i], tie == 0u ? 1u : 0u);
+            const uint32_t t = phase_b_redo_block(F, P.saw, (size_t)eb_off[i] << 3, eb_p[i], tie == 0u ? 1u : 0u);
             if (tie == 0u) tie = t;
         }
         eb_n = 0;
     };
     const uint32_t n1f = n1 & ~7u;                  // whole blocks; only an utterance's last chunk has a ragged tail
-    __shared__ __align__(16) unsigned char ring_mem[PH_RING_BYTES];
-    __shared__ __align__(8) uint64_t ring_bar[PH_LANES * PH_ROWS];
-    PhRing ring = ph_ring_init(ring_mem, ring_bar);
-    stream_blocks(ring, F, n0, n1f, [&](uint32_t blk, const float (&f)[8]) -> bool {
+    walk_blocks(F, U, CL, n0, n1f, [&](uint32_t blk, size_t off, const float (&f)[8]) -> bool {
         float pv[8], s[8];
         bool edge = false;
 #pragma unroll
@@ -564,11 +548,11 @@ __global__ void __launch_bounds__(128, PH_OCC) k_phase_b(PlanDev P, uint32_t rou
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             s[k] = fmaf(2.0f, pv[k], -1.0f);                                    // :517 with polyblep = 0 (2p is exact)
-            edge |= !((pv[k] >= f[k]) && (pv[k] <= ssub(1.0f, f[k]))) || !(p >= pv[k]);
+            edge |= !((pv[k] >= f[k]) && (pv[k] <= ssub(1.0f, f[k]))) || !(p >= pv[k]);   // (second test: any wrap inside the block, or a NaN: its tie test)
         }
-        stg256(P.saw + saw_index(dst_item, dst_j, CL), s);
+        stg256(P.saw + off, s);
         if (edge) {                                          // noted; redone after the walk (or when the note pad is full)
-            eb_blk[eb_n] = blk;
+            eb_off[eb_n] = (uint32_t)(off >> 3);
             eb_p[eb_n] = pv[0];
             if (++eb_n == PH_EDGE_BUF) flush();
         }
@@ -576,18 +560,19 @@ __global__ void __launch_bounds__(128, PH_OCC) k_phase_b(PlanDev P, uint32_t rou
 #pragma unroll
             for (int k = 0; k < 8; ++k) dbg[blk + k] = pv[k];
         }
-        dst_j += 8;
-        if (dst_j >= CL) { dst_j = 0; dst_item += item_stride; }
         return true;
     });
     flush();
     if (n1f < n1) {                                  // the ragged tail, sample by sample (the rest of its sector is zeroed)
-        float* dst = P.saw + saw_index(dst_item, dst_j, CL);
+        TileCursor tc;
+        tc.seek(U, n1f, CL);
+        const float* fsrc = F + tc.off;
+        float* dst = P.saw + tc.off;
 #pragma unroll 1
         for (uint32_t t = n1f; t < n1f + 8u; ++t) {
             float sv = 0.0f;
             if (t < n1) {
-                const float f = F[t], pv = p;
+                const float f = fsrc[t - n1f], pv = p;
                 float gk;
                 p = phase_step(p, f, gk);
                 sv = fmaf(2.0f, pv, -1.0f);
@@ -600,7 +585,7 @@ __global__ void __launch_bounds__(128, PH_OCC) k_phase_b(PlanDev P, uint32_t rou
     }
     pcf(P, PCF_END)[g] = p;
     pci(P, PCF_FLAGS)[g] = (int32_t)tie;
-    if (c + 1 == U.pc_count) P.utt_final[(size_t)u * 32 + 24] = p;   // Synthesize.phase after the last sample (stream state)
+    if (X.c + 1 == X.C) P.utt_final[(size_t)X.u * 32 + 24] = p;   // Synthesize.phase after the last sample (stream state)
     const unsigned act = __activemask();
     if ((threadIdx.x & 31) == (unsigned)(__ffs(act) - 1)) atomicAdd(P.pstats + PSTAT_WALKS, (uint32_t)__popc(act));
 }

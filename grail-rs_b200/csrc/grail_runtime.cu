@@ -49,8 +49,8 @@ struct grail_ctx {
     int pscan_cost_model = 1;        // 0: scan every utterance >= pscan_min (at most 16), whatever it costs
     int      zero_copy_out = 0;      // 1: k_formant stores straight into pinned host output (measured slower: 23 vs 50 GB/s over PCIe)
     int      formants_per_lane = 2;  // 1 or 2 formants of an utterance share one lane's clocks, noise and saw
-    int      phase_mode = 0;         // 1: chunk-parallel exact carrier phase (grail_phase.cuh); 0: serial chains (+ phase scan for long utterances)
-    uint32_t phase_chunk = 2048;     // samples per phase chunk (multiple of 256)
+    int      phase_mode = 1;         // 1: chunk-parallel exact carrier phase (grail_phase.cuh); 0: serial chains (+ phase scan for long utterances)
+    uint32_t phase_chunk = 0;        // samples per phase chunk (multiple of 256; 0: chosen by the planner)
     int      phase_rounds = -1;      // repair rounds enqueued after the first proof (-1: by the longest utterance)
     // pinned staging for pageable D2H
     void*    stage[2] = { nullptr, nullptr };
@@ -158,7 +158,7 @@ struct grail_plan {
     std::vector<uint32_t> pscan_utt;
     uint32_t* d_pscan_status = nullptr;
     float* d_pchunks = nullptr; uint32_t pc_stride = 0; double* d_bsum = nullptr; uint32_t* d_utt_status = nullptr; uint32_t* d_pstats = nullptr;
-    uint32_t n_pchunks = 0, phase_chunk = 0, max_pchunks = 0;   // phase_chunk == 0: serial chains only
+    uint32_t n_pchunks = 0, phase_chunk = 0, max_pchunks = 0, pc_per_item = 1;   // phase_chunk == 0: serial chains only
     bool select_on_device = false;   // d_elems was written by k_select from phoneme-level input
     std::vector<void*> pscan_bufs;
     bool jit_on_host = false;   // few distinct jitter increments: schedules computed by the planner
@@ -383,6 +383,8 @@ static PlanDev plan_dev(const grail_plan* pl, bool with_dbg, int slot = 0)
     P.phase_chunk = pl->phase_chunk;
     P.n_pchunks = pl->n_pchunks;
     P.pc_stride = pl->pc_stride;
+    P.pc_per_item = pl->pc_per_item;
+    P.f_tiled = pl->phase_chunk ? 1u : 0u;
     P.n_utts = pl->n_utts; P.n_items = pl->n_items; P.n_groups = pl->n_groups; P.n_jscheds = pl->n_jscheds;
     P.chunk_len = pl->chunk_len;
     P.out_channels = pl->out_channels;
@@ -498,23 +500,6 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
     }
     pl->total_samples = total;
     pl->f_words = f_words + 256;
-    // chunk-parallel exact phase: chunks of PC samples, numbered utterance by utterance
-    pl->phase_chunk = ctx->phase_mode ? std::max<uint32_t>(256u, (ctx->phase_chunk + 255u) & ~255u) : 0u;
-    if (pl->phase_chunk) {
-        uint64_t npc = 0;
-        for (uint32_t u = 0; u < n_utts; ++u) {
-            UttDev& U = pl->utts[u];
-            U.pc_first = (uint32_t)npc;
-            U.pc_count = (U.n_samples + pl->phase_chunk - 1) / pl->phase_chunk;
-            npc += U.pc_count;
-            pl->max_pchunks = std::max(pl->max_pchunks, U.pc_count);
-        }
-        if (npc > 0xFFFFFFF0ull) {
-            plan_release(pl);
-            return set_err(ctx, GRAIL_ERR_UNSUPPORTED, "too many phase chunks");
-        }
-        pl->n_pchunks = (uint32_t)npc;
-    }
     pl->fpt = (uint32_t)ctx->formants_per_lane;
     pl->nw = (nw + pl->fpt - 1) / pl->fpt;   // warps per CTA: ceil(active formants / formants per lane)
     nw = pl->nw;
@@ -633,6 +618,46 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
     pl->n_groups = (pl->n_items + 31) / 32;
     pl->saw_words = (uint64_t)pl->n_groups * 32ull * pl->chunk_len;
 
+    // ---- chunk-parallel exact phase (grail_phase.cuh): every work item is cut into K phase chunks of PC samples, a
+    //      multiple of 256; an utterance's chunks are numbered in time order.  PC "auto": enough chunks for about 16
+    //      warps of walks per SM (the walks are streaming kernels), at least 1024 samples (a chunk without a carrier
+    //      wrap has no anchor: shorter chunks fail their proofs more often), at most 4096.
+    pl->phase_chunk = 0;
+    if (ctx->phase_mode && pl->n_items) {
+        uint64_t pc = ctx->phase_chunk;
+        if (pc == 0) {
+            const uint64_t lanes = (uint64_t)ctx->prop.multiProcessorCount * 16ull * 32ull;
+            pc = std::min<uint64_t>(4096, std::max<uint64_t>(1024, (total / lanes) & ~255ull));
+        }
+        pc = std::max<uint64_t>(256, (pc + 255) & ~255ull);
+        pc = std::min<uint64_t>(pc, pl->chunk_len);
+        pl->phase_chunk = (uint32_t)pc;
+        pl->pc_per_item = (pl->chunk_len + pl->phase_chunk - 1) / pl->phase_chunk;
+        uint64_t npc = 0;
+        for (uint32_t u = 0; u < n_utts; ++u) {
+            UttDev& U = pl->utts[u];
+            U.pc_first = (uint32_t)npc;
+            U.pc_count = 0;
+            if (U.n_samples) {
+                const uint32_t full = (U.n_samples - 1) / pl->chunk_len;              // items before the last one
+                const uint32_t tail = U.n_samples - full * pl->chunk_len;              // samples of the last item
+                U.pc_count = full * pl->pc_per_item + (tail + pl->phase_chunk - 1) / pl->phase_chunk;
+            }
+            npc += U.pc_count;
+            pl->max_pchunks = std::max(pl->max_pchunks, U.pc_count);
+        }
+        if (npc > 0xFFFFFFF0ull || (uint64_t)pl->n_groups * pl->pc_per_item > 0x7FFFFFFull) {
+            plan_release(pl);
+            return set_err(ctx, GRAIL_ERR_UNSUPPORTED, "too many phase chunks");
+        }
+        pl->n_pchunks = (uint32_t)npc;
+        // F_t shares the saw's tiled layout; the tiled offsets are noted in units of 8 floats in 32 bits
+        if (pl->saw_words >= (1ull << 35)) {
+            plan_release(pl);
+            return set_err(ctx, GRAIL_ERR_UNSUPPORTED, "batch too large for one plan (2^35 scratch words)");
+        }
+    }
+
     // ---- long utterances: exact parallel phase scan instead of the serial chain.  The chains of k_phase_pair run
     //      concurrently, so that kernel lasts as long as its longest utterance (4.7 ns/sample measured); a scan costs
     //      about 0.40 ms of launches plus 0.125 ns/sample and scans run one after another.  Take the k longest
@@ -684,7 +709,9 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
     PA(pl->d_items, std::max<size_t>(pl->n_items, 1) * sizeof(ItemDev));
     PA(pl->d_jscheds, std::max<size_t>(pl->n_jscheds, 1) * sizeof(JitSchedDev));
     PA(pl->d_jrecs, std::max<size_t>(pl->n_jrecs, 1) * sizeof(JitRec));
-    PA(pl->d_F, pl->f_words * sizeof(float));
+    // (F_t of a chunk-parallel plan is tiled like the saw)
+    const uint64_t F_words = pl->phase_chunk ? std::max<uint64_t>(pl->saw_words, 8) + 256 : pl->f_words;
+    PA(pl->d_F, F_words * sizeof(float));
     PA(pl->d_fflags, (pl->f_words / 128 + 2) * sizeof(uint32_t));
     PA(pl->d_saw, std::max<uint64_t>(pl->saw_words, 8) * sizeof(float));
     PA(pl->d_err, 256);
@@ -777,7 +804,7 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
     for (auto& e : pl->ev) CUF(cudaEventCreate(&e));
     pl->slot[0].F = pl->d_F; pl->slot[0].fflags = pl->d_fflags; pl->slot[0].saw = pl->d_saw;
     if (pl->pipelined) {
-        PA(pl->slot[1].F, pl->f_words * sizeof(float));
+        PA(pl->slot[1].F, F_words * sizeof(float));
         PA(pl->slot[1].fflags, (pl->f_words / 128 + 2) * sizeof(uint32_t));
         PA(pl->slot[1].saw, std::max<uint64_t>(pl->saw_words, 8) * sizeof(float));
         CUF(cudaEventCreateWithFlags(&pl->ev_begin, cudaEventDisableTiming));
@@ -839,6 +866,7 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
     cudaStream_t s = sf;
     pl->last_launches = 0;
     CU(ctx, cudaMemsetAsync(pl->d_err, 0, 4, s));
+    CU(ctx, cudaMemsetAsync(pl->d_pstats, 0, 256, s));
     CU(ctx, cudaEventRecord(ev[0], s));
     if (pl->n_items && !pl->jit_on_host) {
         k_jitter_schedule<<<(pl->n_jscheds + 63) / 64, 64, 0, s>>>(P);
@@ -885,8 +913,8 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
     }
     if (pl->n_items && pl->phase_chunk) {
         // chunk-parallel exact phase (grail_phase.cuh): guess, round A, scan, round B, then proof / repair rounds
-        const unsigned wg = (unsigned)(((uint64_t)pl->n_utts * 32 + 127) / 128), cg = (pl->n_pchunks + 127) / 128;
-        CU(ctx, cudaMemsetAsync(pl->d_pstats, 0, 256, s));
+        const unsigned wg = (unsigned)(((uint64_t)pl->n_utts * 32 + 127) / 128);
+        const unsigned cg = (unsigned)(((uint64_t)pl->n_groups * pl->pc_per_item + 3) / 4);   // a warp = one sub-range of one group of 32 items
         k_phase_guess<<<wg, 128, 0, s>>>(P);
         pl->last_launches++;
         if (pl->max_pchunks > 1) {
@@ -1070,7 +1098,7 @@ int grail_cuda_set_option(grail_ctx* ctx, const char* key, double value)
     } else if (!strcmp(key, "phase_mode")) {
         ctx->phase_mode = value != 0.0;
     } else if (!strcmp(key, "phase_chunk")) {
-        if (!(value >= 256.0 && value <= 1048576.0)) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "phase_chunk out of range [256, 2^20]");
+        if (value != 0.0 && !(value >= 256.0 && value <= 1048576.0)) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "phase_chunk out of range [256, 2^20] (0 = auto)");
         ctx->phase_chunk = (uint32_t)value;
     } else if (!strcmp(key, "phase_rounds")) {
         ctx->phase_rounds = value < 0.0 ? -1 : (value > PH_MAX_ROUNDS ? PH_MAX_ROUNDS : (int)value);
@@ -1301,7 +1329,7 @@ int grail_cuda_plan_phase_stats(grail_plan* plan, uint32_t* stats)
     memset(stats, 0, 8 * sizeof(uint32_t));
     stats[0] = plan->n_pchunks;
     stats[5] = plan->phase_chunk;
-    if (!plan->phase_chunk || !plan->launched) return GRAIL_OK;
+    if (!plan->launched) return GRAIL_OK;
     int rcj = plan_join(plan);
     if (rcj) return rcj;
     uint32_t st[16];
@@ -1311,6 +1339,7 @@ int grail_cuda_plan_phase_stats(grail_plan* plan, uint32_t* stats)
     stats[2] = st[PSTAT_UNPROVEN];
     stats[3] = st[PSTAT_ROUNDS];
     stats[4] = st[PSTAT_MISMATCH];
+    stats[6] = st[PSTAT_WARMUP_FROM_ZERO];
     return GRAIL_OK;
 }
 
@@ -1337,20 +1366,22 @@ int grail_cuda_plan_read_intermediates(grail_plan* plan, float* frequency, float
         }
         return GRAIL_OK;
     };
-    if (frequency && (rc = gather_linear(plan->d_F, frequency))) return rc;
-    if (carrier_phase && (rc = gather_linear(plan->d_phase_dbg, carrier_phase))) return rc;
-    if (saw) {
-        CU(ctx, cudaMemcpy(tmp.data(), plan->slot[0].saw, plan->saw_words * sizeof(float), cudaMemcpyDeviceToHost));
+    auto gather_tiled = [&](const float* dsrc, float* dst) -> int {
+        CU(ctx, cudaMemcpy(tmp.data(), dsrc, plan->saw_words * sizeof(float), cudaMemcpyDeviceToHost));
         const uint32_t CL = plan->chunk_len;
         for (uint32_t u = 0; u < plan->n_utts; ++u) {
             const UttDev& U = plan->utts[u];
             for (uint32_t n = 0; n < U.n_samples; ++n) {
                 const uint32_t item = U.item_first + (n / CL) * U.item_stride, j = n % CL;
                 const size_t idx = ((size_t)(item >> 5) * (CL >> 3) + (j >> 3)) * 256u + (item & 31u) * 8u + (j & 7u);
-                saw[U.out_off + n] = tmp[idx];
+                dst[U.out_off + n] = tmp[idx];
             }
         }
-    }
+        return GRAIL_OK;
+    };
+    if (frequency && (rc = plan->phase_chunk ? gather_tiled(plan->d_F, frequency) : gather_linear(plan->d_F, frequency))) return rc;
+    if (carrier_phase && (rc = gather_linear(plan->d_phase_dbg, carrier_phase))) return rc;
+    if (saw && (rc = gather_tiled(plan->slot[0].saw, saw))) return rc;
     return GRAIL_OK;
 }
 
@@ -1555,6 +1586,48 @@ int grail_cuda_stream_pull(grail_stream* s, float* out, uint64_t max_samples, ui
 void grail_cuda_stream_free(grail_stream* s) { delete s; }
 
 // ---- roofline probes ---------------------------------------------------------------------------
+int grail_cuda_copy_segments(grail_ctx* ctx, void* dst, const void* src, const uint64_t* dst_off, const uint64_t* src_off,
+                             const uint64_t* len, uint64_t n_segments, uint32_t elem_bytes)
+{
+    if (!ctx) return GRAIL_ERR_INVALID_ARG;
+    if (elem_bytes != 2 && elem_bytes != 4) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "elem_bytes must be 2 or 4");
+    if (n_segments == 0) return GRAIL_OK;
+    if (!dst || !src || !dst_off || !src_off || !len) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "null pointer");
+    CU(ctx, cudaSetDevice(ctx->device));
+    std::vector<SegCopy> segs(n_segments);
+    std::vector<uint32_t> tile_seg, tile_idx;
+    for (uint64_t i = 0; i < n_segments; ++i) {
+        segs[i].dst = dst_off[i] * elem_bytes; segs[i].src = src_off[i] * elem_bytes; segs[i].len = len[i] * elem_bytes;
+        const uint64_t tiles = (segs[i].len + SEG_TILE_BYTES - 1) / SEG_TILE_BYTES;
+        if (i > 0xFFFFFFF0ull || tiles > 0xFFFFFFF0ull || tile_seg.size() + tiles > 0x7FFFFFF0ull)
+            return set_err(ctx, GRAIL_ERR_UNSUPPORTED, "too many segments / tiles for one call");
+        for (uint64_t t = 0; t < tiles; ++t) { tile_seg.push_back((uint32_t)i); tile_idx.push_back((uint32_t)t); }
+    }
+    if (tile_seg.empty()) return GRAIL_OK;
+    void *d_segs = nullptr, *d_ts = nullptr, *d_ti = nullptr;
+    int rc = pool_alloc(ctx, segs.size() * sizeof(SegCopy), &d_segs);
+    if (!rc) rc = pool_alloc(ctx, tile_seg.size() * 4, &d_ts);
+    if (!rc) rc = pool_alloc(ctx, tile_idx.size() * 4, &d_ti);
+    if (!rc) {
+        cudaStream_t s = ctx->stream;
+        cudaError_t e = cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(SegCopy), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_ts, tile_seg.data(), tile_seg.size() * 4, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_ti, tile_idx.data(), tile_idx.size() * 4, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) {
+            k_copy_segments<<<(unsigned)tile_seg.size(), 256, 0, s>>>((unsigned char*)dst, (const unsigned char*)src,
+                                                                       (const SegCopy*)d_segs, (const uint32_t*)d_ts,
+                                                                       (const uint32_t*)d_ti, elem_bytes);
+            e = cudaGetLastError();
+        }
+        // the tables are pageable host vectors: the copies above have been staged by the time the calls return, but the
+        // scratch buffers go back to the pool, so the launch must have consumed them first
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = set_err(ctx, GRAIL_ERR_CUDA, "segment copy failed: %s", cudaGetErrorString(e));
+    }
+    pool_free(ctx, d_segs); pool_free(ctx, d_ts); pool_free(ctx, d_ti);
+    return rc;
+}
+
 int grail_cuda_probe_fp32_peak(grail_ctx* ctx, double* ffma_flops, double* mufu_ops, double* sm_mhz_effective)
 {
     if (!ctx) return GRAIL_ERR_INVALID_ARG;

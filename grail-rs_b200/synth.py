@@ -214,6 +214,13 @@ class Context:
         self._check(self._L.grail_cuda_probe_fp32_peak(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return {"ffma_flops": a.value, "mufu_ops": b.value, "sm_mhz_effective": c.value}
 
+    def copy_segments(self, d_dst: int, d_src: int, dst_off: np.ndarray, src_off: np.ndarray, lengths: np.ndarray,
+                      elem_bytes: int = 4):
+        """device segment copy (grail_cuda_copy_segments): the reorder step of a multi-GPU output gather"""
+        d, s_, l = (np.ascontiguousarray(x, np.uint64) for x in (dst_off, src_off, lengths))
+        self._check(self._L.grail_cuda_copy_segments(self._h, C.c_void_p(d_dst), C.c_void_p(d_src), ptr(d), ptr(s_), ptr(l),
+                                                     len(l), int(elem_bytes)))
+
     # -- one-shot (host buffers in, host buffer out): the drop-in for draining the iterator chain
     def synthesize_batch(self, elems: np.ndarray, utt_offsets: np.ndarray, voices: np.ndarray,
                          out: Optional[np.ndarray] = None, out_offsets: Optional[np.ndarray] = None, fmt: int = _ffi.F32):
@@ -335,7 +342,7 @@ class Plan:
         st = np.zeros(8, np.uint32)
         self.ctx._check(self._L.grail_cuda_plan_phase_stats(self._h, ptr(st)))
         return {"chunks": int(st[0]), "walks": int(st[1]), "unproven_utterances": int(st[2]), "repair_rounds": int(st[3]),
-                "failed_boundaries": int(st[4]), "phase_chunk": int(st[5])}
+                "failed_boundaries": int(st[4]), "phase_chunk": int(st[5]), "warmup_from_zero": int(st[6])}
 
     def read_intermediates(self):
         """bit-exact taps: (F_t, carrier phase before each sample, polyBLEP saw), packed like the output"""

@@ -122,3 +122,18 @@ def parity_stats(got: np.ndarray, want: np.ndarray) -> dict:
     den = float(np.sum(err * err))
     snr = float("inf") if den == 0.0 else (-float("inf") if num == 0.0 else 10.0 * np.log10(num / den))
     return {"max_abs": float(np.max(np.abs(err))) if len(err) else 0.0, "snr_db": snr}
+
+
+def parity_batch(got: np.ndarray, want: np.ndarray, out_offsets: np.ndarray) -> dict:
+    """worst per-utterance max-abs error and SNR of a packed batch against the reference waveforms (same packing)"""
+    worst = {"max_abs": 0.0, "snr_db": float("inf"), "worst_utt": -1, "n_utts": len(out_offsets) - 1}
+    for u in range(len(out_offsets) - 1):
+        a, b = int(out_offsets[u]), int(out_offsets[u + 1])
+        if a == b:
+            continue
+        st = parity_stats(got[a:b], want[a:b])
+        if st["max_abs"] > worst["max_abs"] or st["snr_db"] < worst["snr_db"]:
+            worst["worst_utt"] = u
+        worst["max_abs"] = max(worst["max_abs"], st["max_abs"])
+        worst["snr_db"] = min(worst["snr_db"], st["snr_db"])
+    return worst

@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 #define GRAIL_NUM_FORMANTS 8 /* reference NUM_FORMANTS, src/lib.rs:24 */
-#define GRAIL_ABI_VERSION 3   /* 2: phoneme-level plans, grail_cuda_transcribe_batch; 3: grail_cuda_plan_phase_stats */
+#define GRAIL_ABI_VERSION 4   /* 2: phoneme-level plans, grail_cuda_transcribe_batch; 3: grail_cuda_plan_phase_stats; 4: grail_cuda_copy_segments */
 
 typedef enum grail_status {
     GRAIL_OK = 0,
@@ -219,7 +219,10 @@ int  grail_cuda_plan_phase_scan_stats(grail_plan* plan, uint32_t* stats);
  * shifted and walked again for up to option "phase_rounds" rounds, and an utterance that is still unproven then gets the
  * serial chain.  stats[8] of the most recent launch = {phase chunks in the plan, chunks walked in all rounds together,
  * utterances that fell back to the serial chain, last repair round that was needed (0 = none), chunk boundaries that
- * failed a proof, phase_chunk, 0, 0}. */
+ * failed a proof, phase_chunk, W, 0}, where W counts the (time chunk, formant) pairs of the filter kernel whose
+ * decay-bounded warm-up reached all the way back to sample 0: a formant that rings longer than the utterance has lasted
+ * is recomputed from the start by every later chunk (exact, but its time parallelism is gone -- a performance cliff
+ * that would otherwise be silent; 0 for ordinary voices). */
 int  grail_cuda_plan_phase_stats(grail_plan* plan, uint32_t* stats);
 /* debug / parity taps, host buffers of total_samples entries; any may be NULL:
  * the bit-exact fundamental F_t, the carrier phase BEFORE each sample, and the polyBLEP saw */
@@ -238,6 +241,15 @@ int  grail_cuda_stream_push(grail_stream* s, const grail_seq_elem* elems, uint32
 int  grail_cuda_stream_finish(grail_stream* s);
 int  grail_cuda_stream_pull(grail_stream* s, float* out, uint64_t max_samples, uint64_t* n_written);
 void grail_cuda_stream_free(grail_stream* s);
+
+/* ---- multi-GPU output gather helper ("optional gather of outputs to one rank") ----------------------------
+ * Utterances are sharded over devices (one ctx each) and every shard's output is packed in ITS utterance order; after
+ * the caller's all-gather (NCCL) this puts the pieces back in the order of the whole batch: n_segments copies
+ * dst[dst_off[i] .. dst_off[i] + len[i]) = src[src_off[i] .. src_off[i] + len[i]), offsets and lengths in ELEMENTS of
+ * elem_bytes (4: f32, 2: i16).  dst and src are DEVICE pointers on ctx's device; the three tables are HOST arrays.
+ * One kernel launch on the ctx stream (asynchronous; segments must not overlap in dst). */
+int  grail_cuda_copy_segments(grail_ctx* ctx, void* dst, const void* src, const uint64_t* dst_off, const uint64_t* src_off,
+                              const uint64_t* len, uint64_t n_segments, uint32_t elem_bytes);
 
 /* ---- roofline probes (used by bench.py; device microbenchmarks, not part of the path) -------- */
 /* dense FFMA issue rate of this device, in FP32 flop/s (2 per FFMA), and MUFU.RCP rate in op/s */

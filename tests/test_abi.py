@@ -33,7 +33,7 @@ def test_struct_layout_matches_header():
     assert g.ELEM_DT.itemsize == 196 and g.SEQ_ELEM_DT.itemsize == 208 and g.VOICE_DT.itemsize == 28
     assert g.SEQ_ELEM_DT.fields["length"][1] == 200 and g.SEQ_ELEM_DT.fields["blend_length"][1] == 204
     assert g.SEQ_ELEM_DT.fields["elem"][1] == 4
-    assert g._ffi.lib().grail_cuda_abi_version() == 3
+    assert g._ffi.lib().grail_cuda_abi_version() == 4
 
 
 def test_status_strings():

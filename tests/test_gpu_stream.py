@@ -63,3 +63,30 @@ def test_stream_incremental_push_holds_lookahead(ctx, oracle):
     stats = W.parity_stats(got, want)
     assert stats["max_abs"] <= 1e-4 and stats["snr_db"] >= 90.0, stats
     st.close()
+
+
+def test_stream_multi_chunk_window_narrow_bandwidth(ctx, oracle):
+    """windows longer than one time chunk with a voice whose formants ring for tens of thousands of samples (bandwidth
+    3 Hz): every chunk of a window whose warm-up reaches back to the window's first sample must start from the CARRIED
+    filter state, not from rest"""
+    v = g.voices.generic()
+    elems, offs, vp = W.from_phonemes([[3, 4, 3, 4]], v, [3])
+    elems = elems.copy()
+    elems["elem"]["formant_bw"][:] = np.float32(3.0 / 44100.0)
+    want, _, _ = oracle.synthesize(elems, vp[0])
+    ctx.set_option("min_chunk", 2048)
+    st = ctx.stream(vp[0])
+    st.push(elems)
+    st.finish()
+    got = []
+    while True:
+        x = st.pull(20000)                # ~10 chunks of 2 048 per window
+        if len(x) == 0:
+            break
+        got.append(x.copy())
+    got = np.concatenate(got)
+    assert len(got) == len(want)
+    stats = W.parity_stats(got, want)
+    print(stats)
+    assert stats["max_abs"] <= 1e-4 and stats["snr_db"] >= 90.0, stats
+    st.close()
