@@ -53,7 +53,7 @@ EXPORTS = [
     "grail_cuda_plan_device_output", "grail_cuda_plan_read_output", "grail_cuda_plan_timings",
     "grail_cuda_plan_read_intermediates", "grail_cuda_plan_phase_scan_stats", "grail_cuda_plan_phase_stats", "grail_cuda_stream_new", "grail_cuda_stream_push",
     "grail_cuda_stream_finish", "grail_cuda_stream_pull", "grail_cuda_stream_free", "grail_cuda_probe_fp32_peak",
-    "grail_cuda_copy_segments",
+    "grail_cuda_copy_segments", "grail_cuda_streams_pull",
     "grail_cuda_debug_clock_desc", "grail_cuda_debug_clock_asc", "grail_cuda_debug_lcg_jump",
     "grail_cuda_debug_jitter_index", "grail_cuda_debug_div_check",
 ]
@@ -103,6 +103,7 @@ def lib() -> C.CDLL:
         "grail_cuda_stream_push": (i32, [vp, vp, u32]),
         "grail_cuda_stream_finish": (i32, [vp]),
         "grail_cuda_stream_pull": (i32, [vp, vp, u64, C.POINTER(u64)]),
+        "grail_cuda_streams_pull": (i32, [vp, u32, vp, vp, vp]),
         "grail_cuda_stream_free": (None, [vp]),
         "grail_cuda_copy_segments": (i32, [vp, vp, vp, vp, vp, vp, u64, u32]),
         "grail_cuda_probe_fp32_peak": (i32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -52,10 +52,9 @@ struct grail_ctx {
     int      phase_mode = 1;         // 1: chunk-parallel exact carrier phase (grail_phase.cuh); 0: serial chains (+ phase scan for long utterances)
     uint32_t phase_chunk = 0;        // samples per phase chunk (multiple of 256; 0: chosen by the planner)
     int      phase_rounds = -1;      // repair rounds enqueued after the first proof (-1: by the longest utterance)
-    // pinned staging for pageable D2H
-    void*    stage[2] = { nullptr, nullptr };
-    size_t   stage_bytes = 0;
-    cudaEvent_t stage_ev[2] = { nullptr, nullptr };
+    cudaStream_t   s_copy = nullptr;    // one-shot batches: device-to-host copies of finished utterance groups
+    int      e2e_groups = -1;        // one-shot batches: utterance groups whose copies overlap the next group's kernels (-1 auto)
+    std::vector<grail_plan*> live_plans;   // plans created on this ctx and not yet destroyed (synchronize clears their in_flight)
 };
 
 static int set_err(grail_ctx* ctx, int status, const char* fmt, ...)
@@ -396,6 +395,7 @@ static void plan_release(grail_plan* pl)
 {
     if (!pl) return;
     grail_ctx* ctx = pl->ctx;
+    ctx->live_plans.erase(std::remove(ctx->live_plans.begin(), ctx->live_plans.end(), pl), ctx->live_plans.end());
     void* bufs[] = { pl->d_elems, pl->d_segs, pl->d_utts, pl->d_items, pl->d_jscheds, pl->d_jrecs, pl->d_F, pl->d_saw,
                      pl->d_phase_dbg, pl->d_err, pl->d_out, pl->d_fflags, pl->d_utt_init, pl->d_utt_final,
                      pl->d_pchunks, pl->d_bsum, pl->d_utt_status, pl->d_pstats };
@@ -418,7 +418,7 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
                       const grail_voice_params* voices, uint32_t n_utts, grail_plan** out_plan,
                       const StreamStart* ss = nullptr, bool pipelined = false)
 {
-    if (ss && n_utts != 1) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "a stream window is one utterance");
+    // (ss: one StreamStart per utterance -- the windows of n_utts concurrent streams share one plan and one launch)
     int rc = validate_inputs(ctx, in, utt_offsets, voices, n_utts);
     if (rc) return rc;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -434,7 +434,10 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
 
     // ---- exact schedule + active formants
     SeqCache cache;
-    std::unordered_map<uint32_t, uint32_t> jmap;
+    std::unordered_map<uint64_t, uint32_t> jmap;
+    std::vector<float> init_states;                  // continued streams: 32 floats per utterance
+    if (ss) init_states.assign((size_t)std::max<uint32_t>(n_utts, 1) * 32, 0.0f);
+    const StreamStart* const ss_all = ss;
     uint32_t nw = 1;
     uint64_t total = 0, f_words = 0;
     uint32_t n_max = 0;
@@ -444,6 +447,8 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
         U.elem_first = utt_offsets[u];
         U.n_elems = utt_offsets[u + 1] - utt_offsets[u];
         const uint32_t e0 = U.elem_first;
+        const StreamStart* ss = ss_all ? ss_all + u : nullptr;      // this utterance's carried state
+        if (ss && ss->filter_state) memcpy(init_states.data() + (size_t)u * 32, ss->filter_state, 24 * sizeof(float));
         int64_t n = schedule_utterance_fn([&in, e0](uint32_t p) { return in.length(e0 + p); }, U.n_elems, voices[u].sample_rate,
                                           pl->segs.data() + U.elem_first, cache, ss);
         if (n >= 0 && ss) {
@@ -481,8 +486,8 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
             if (act) U.active[U.n_active++] = (uint8_t)i;
         }
         nw = std::max(nw, U.n_active);
-        // jitter schedules are shared by every utterance with the same increment
-        const uint32_t key = f2u(voices[u].jitter_frequency);
+        // jitter schedules are shared by every utterance with the same increment (and, for streams, the same phase)
+        const uint64_t key = (uint64_t)f2u(voices[u].jitter_frequency) | ((uint64_t)f2u(ss ? ss->jitter_phase : 0.0f) << 32);
         auto jt = jmap.find(key);
         if (jt == jmap.end()) {
             JitSchedDev js;
@@ -517,7 +522,7 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
     pl->n_jrecs = (uint32_t)n_jrecs;
     // a handful of distinct increments (the common case: one voice) is cheaper on the host than a
     // latency-bound single-lane kernel; thousands (per-utterance voices) go to k_jitter_schedule
-    if (pl->n_jscheds <= 64) {
+    if (pl->n_jscheds <= 64 || ss_all) {   // (stream windows: always, the host needs the schedule for the carried state)
         pl->jit_on_host = true;
         pl->jrecs.resize(std::max<uint32_t>(pl->n_jrecs, 1));
         for (auto& js : pl->jscheds) {
@@ -789,16 +794,13 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
     if (pl->n_jscheds) CUF(cudaMemcpyAsync(pl->d_jscheds, pl->jscheds.data(), pl->n_jscheds * sizeof(JitSchedDev), cudaMemcpyHostToDevice, s));
     if (pl->jit_on_host && pl->n_jrecs) CUF(cudaMemcpyAsync(pl->d_jrecs, pl->jrecs.data(), (size_t)pl->n_jrecs * sizeof(JitRec), cudaMemcpyHostToDevice, s));
     {
-        float init[32];
-        memset(init, 0, sizeof init);
-        if (ss && ss->filter_state) memcpy(init, ss->filter_state, 24 * sizeof(float));
         CUF(cudaMemsetAsync(pl->d_utt_init, 0, std::max<size_t>(n_utts, 1) * 32 * sizeof(float), s));
         CUF(cudaMemsetAsync(pl->d_utt_final, 0, std::max<size_t>(n_utts, 1) * 32 * sizeof(float), s));
         CUF(cudaMemsetAsync(pl->d_utt_status, 0, std::max<size_t>(n_utts, 1) * sizeof(uint32_t), s));
         CUF(cudaMemsetAsync(pl->d_pstats, 0, 256, s));
         if (ss) {   // formants nobody touches in this window keep their carried state
-            CUF(cudaMemcpyAsync(pl->d_utt_init, init, sizeof init, cudaMemcpyHostToDevice, s));
-            CUF(cudaMemcpyAsync(pl->d_utt_final, init, sizeof init, cudaMemcpyHostToDevice, s));
+            CUF(cudaMemcpyAsync(pl->d_utt_init, init_states.data(), init_states.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+            CUF(cudaMemcpyAsync(pl->d_utt_final, init_states.data(), init_states.size() * sizeof(float), cudaMemcpyHostToDevice, s));
         }
     }
     for (auto& e : pl->ev) CUF(cudaEventCreate(&e));
@@ -818,6 +820,7 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
     CUF(cudaStreamSynchronize(s));
 #undef PA
 #undef CUF
+    ctx->live_plans.push_back(pl);
     *out_plan = pl;
     return GRAIL_OK;
 }
@@ -1030,15 +1033,15 @@ int grail_cuda_create(int device, grail_ctx** out_ctx)
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithPriority(&ctx->s_front, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
-        cudaStreamCreateWithPriority(&ctx->s_back, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
+        cudaStreamCreateWithPriority(&ctx->s_back, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking) != cudaSuccess) {
         cudaGetLastError();
-        delete ctx;
+        grail_cuda_destroy(ctx);             // destroys whichever streams were created
         return GRAIL_ERR_CUDA;
     }
     if (ctx->prop.major < 10) {
         // built for sm_100a only; an older device cannot run the cubin
-        cudaStreamDestroy(ctx->stream);
-        delete ctx;
+        grail_cuda_destroy(ctx);
         return GRAIL_ERR_NO_DEVICE;
     }
     *out_ctx = ctx;
@@ -1049,16 +1052,14 @@ void grail_cuda_destroy(grail_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->s_front) { cudaStreamSynchronize(ctx->s_front); cudaStreamDestroy(ctx->s_front); }
     if (ctx->s_back) { cudaStreamSynchronize(ctx->s_back); cudaStreamDestroy(ctx->s_back); }
+    if (ctx->s_copy) { cudaStreamSynchronize(ctx->s_copy); cudaStreamDestroy(ctx->s_copy); }
     for (auto& b : ctx->pool)
         if (b.ptr) cudaFree(b.ptr);
-    for (int i = 0; i < 2; ++i) {
-        if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
-        if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
-    }
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    cudaGetLastError();
     delete ctx;
 }
 
@@ -1072,7 +1073,11 @@ int grail_cuda_synchronize(grail_ctx* ctx)
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaStreamSynchronize(ctx->s_front));
     CU(ctx, cudaStreamSynchronize(ctx->s_back));
+    CU(ctx, cudaStreamSynchronize(ctx->s_copy));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    // everything has drained: the next pipelined launch of any plan is again "the first of a burst" and orders itself
+    // after whatever the caller queues on the main stream from now on
+    for (grail_plan* pl : ctx->live_plans) pl->in_flight = false;
     return GRAIL_OK;
 }
 
@@ -1095,6 +1100,8 @@ int grail_cuda_set_option(grail_ctx* ctx, const char* key, double value)
         ctx->pipeline = value != 0.0;
     } else if (!strcmp(key, "phase_lean")) {
         ctx->phase_lean = value < 0.0 ? -1 : (value != 0.0);
+    } else if (!strcmp(key, "e2e_groups")) {
+        ctx->e2e_groups = value < 0.0 ? -1 : (int)value;
     } else if (!strcmp(key, "phase_mode")) {
         ctx->phase_mode = value != 0.0;
     } else if (!strcmp(key, "phase_chunk")) {
@@ -1246,6 +1253,8 @@ int grail_cuda_plan_device_output(grail_plan* plan, int format, void** out_dptr)
     const size_t need = (size_t)std::max<uint64_t>(plan->total_samples, 1) * format_bytes(format);
     if (!plan->d_out || plan->d_out_bytes < need) {
         if (plan->d_out) {
+            int rcj = plan_join(plan);           // a pipelined formant kernel may still be writing the old buffer
+            if (rcj) return rcj;
             CU(ctx, cudaStreamSynchronize(ctx->stream));
             pool_free(ctx, plan->d_out);
             plan->d_out = nullptr;
@@ -1387,35 +1396,52 @@ int grail_cuda_plan_read_intermediates(grail_plan* plan, float* frequency, float
 
 } // extern "C"
 
+// One-shot batches with HOST output: the batch is cut into a few utterance groups of geometrically growing size
+// (1 : 4 : 16), each its own plan; group k's device-to-host copy runs on the copy stream while group k+1's kernels run,
+// and the host builds plan k+1 while the device works on k.  PCIe is the bound of this call (0.9 GB at ~52 GB/s = 17 ms
+// against 3 ms of kernels at config 2), so what matters is that the first copy starts early and the copy engine never
+// waits: the small first group gets the copy stream going after a fraction of a millisecond.  Groups are contiguous
+// in utterance order, so every group's samples are one contiguous range of `out`.
+static void split_groups(const uint64_t* out_offsets, uint32_t n_utts, int want, size_t elem_bytes, std::vector<uint32_t>& bounds)
+{
+    bounds.clear();
+    bounds.push_back(0);
+    const uint64_t total = out_offsets[n_utts] - out_offsets[0];
+    int G = want;
+    if (G < 0) G = (n_utts >= 96 && total * elem_bytes >= (48ull << 20)) ? 3 : 1;
+    G = std::max(1, std::min(G, 8));
+    if (G > 1) {
+        double denom = 0.0, w = 1.0;
+        for (int g = 0; g < G; ++g) { denom += w; w *= 4.0; }
+        double acc = 0.0;
+        w = 1.0;
+        for (int g = 0; g + 1 < G; ++g) {
+            acc += w; w *= 4.0;
+            const uint64_t target = out_offsets[0] + (uint64_t)((double)total * acc / denom);
+            uint32_t u = (uint32_t)(std::lower_bound(out_offsets, out_offsets + n_utts + 1, target) - out_offsets);
+            u = std::min(std::max(u, bounds.back() + 1), n_utts);
+            if (u > bounds.back() && u < n_utts) bounds.push_back(u);
+        }
+    }
+    bounds.push_back(n_utts);
+}
+
 static int synthesize_batch_impl(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_t* utt_offsets,
                                  const grail_voice_params* voices, uint32_t n_utts, int format, void* out,
                                  const uint64_t* out_offsets, int out_is_device)
 {
     if (!ctx) return GRAIL_ERR_INVALID_ARG;
     if (!out_offsets) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "null out_offsets");
-    grail_plan* pl = nullptr;
-    ElemInput in;
-    in.full = elems;
-    int rc = plan_build(ctx, in, utt_offsets, voices, n_utts, &pl);
-    if (rc) return rc;
-    // the caller's layout must be the exact counts, packed in utterance order from out_offsets[0]
-    for (uint32_t u = 0; u < n_utts; ++u) {
-        if (out_offsets[u + 1] - out_offsets[u] != (uint64_t)pl->utts[u].n_samples || out_offsets[u + 1] < out_offsets[u]) {
-            const unsigned long long want = pl->utts[u].n_samples, got = out_offsets[u + 1] - out_offsets[u];
-            plan_release(pl);
-            return set_err(ctx, GRAIL_ERR_COUNT_MISMATCH, "utterance %u yields %llu samples, out_offsets leave room for %llu",
-                           u, want, got);
-        }
-    }
-    if (pl->total_samples && !out) {
-        plan_release(pl);
-        return set_err(ctx, GRAIL_ERR_INVALID_ARG, "null output pointer");
-    }
-    char* base = out ? (char*)out + out_offsets[0] * format_bytes(format) : nullptr;
-    // A pinned (page-locked, device-mapped) host buffer is written by k_formant directly: its 128-byte row stores
-    // cross PCIe as posted writes while the kernel is still computing, so the device-to-host transfer is fully
-    // overlapped and no device-side output buffer is needed.  Measured on B200: 39 ms vs 21 ms per config-2 step for
-    // the copy-engine path (16-byte-per-lane stores use PCIe poorly), so this is opt-in (ctx option "zero_copy_out").
+    if (!utt_offsets || (n_utts && !voices)) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "null input pointer");
+    for (uint32_t u = 0; u < n_utts; ++u)
+        if (utt_offsets[u + 1] < utt_offsets[u]) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "utt_offsets not monotone at %u", u);
+    for (uint32_t u = 0; u < n_utts; ++u)
+        if (out_offsets[u + 1] < out_offsets[u]) return set_err(ctx, GRAIL_ERR_COUNT_MISMATCH, "out_offsets not monotone at %u", u);
+    const size_t eb = format_bytes(format);
+    // A pinned (page-locked, device-mapped) host buffer can be written by k_formant directly (ctx option
+    // "zero_copy_out"): measured on B200 39 ms vs 21 ms per config-2 step for the copy-engine path (16-byte-per-lane
+    // stores use PCIe poorly), so it is opt-in.
+    char* base = out ? (char*)out + out_offsets[0] * eb : nullptr;
     void* mapped = nullptr;
     if (!out_is_device && base && ctx->zero_copy_out) {
         cudaPointerAttributes at;
@@ -1424,17 +1450,61 @@ static int synthesize_batch_impl(grail_ctx* ctx, const grail_seq_elem* elems, co
         else
             cudaGetLastError();
     }
-    if (out_is_device || mapped) {
-        rc = plan_enqueue(pl, mapped ? mapped : (void*)base, format, false, true);
-        if (!rc) rc = plan_check_device_errors(pl);
-    } else {
-        void* d = nullptr;
-        rc = grail_cuda_plan_device_output(pl, format, &d);
-        if (!rc) rc = plan_enqueue(pl, d, format, false, true);
-        if (!rc) rc = grail_cuda_plan_read_output(pl, format, base);
+    const bool direct = out_is_device || mapped;            // the kernels write the caller's buffer themselves
+    std::vector<uint32_t> bounds;
+    split_groups(out_offsets, n_utts, direct ? 1 : ctx->e2e_groups, eb, bounds);
+    std::vector<grail_plan*> plans;
+    std::vector<cudaEvent_t> done;
+    std::vector<uint32_t> offs;
+    int rc = GRAIL_OK;
+    for (size_t g = 0; g + 1 < bounds.size() && !rc; ++g) {
+        const uint32_t u0 = bounds[g], u1 = bounds[g + 1], nu = u1 - u0;
+        offs.resize(nu + 1);
+        for (uint32_t u = 0; u <= nu; ++u) offs[u] = utt_offsets[u0 + u] - utt_offsets[u0];
+        grail_plan* pl = nullptr;
+        ElemInput in;
+        in.full = elems ? elems + utt_offsets[u0] : nullptr;
+        rc = plan_build(ctx, in, offs.data(), voices + u0, nu, &pl);
+        if (rc) break;
+        plans.push_back(pl);
+        // the caller's layout must be the exact counts, packed in utterance order from out_offsets[0]
+        for (uint32_t u = 0; u < nu && !rc; ++u) {
+            if (out_offsets[u0 + u + 1] - out_offsets[u0 + u] != (uint64_t)pl->utts[u].n_samples) {
+                const unsigned long long want = pl->utts[u].n_samples, got = out_offsets[u0 + u + 1] - out_offsets[u0 + u];
+                rc = set_err(ctx, GRAIL_ERR_COUNT_MISMATCH, "utterance %u yields %llu samples, out_offsets leave room for %llu",
+                             u0 + u, want, got);
+            }
+        }
+        if (rc) break;
+        if (pl->total_samples && !out) { rc = set_err(ctx, GRAIL_ERR_INVALID_ARG, "null output pointer"); break; }
+        char* gbase = out ? (char*)out + out_offsets[u0] * eb : nullptr;
+        if (direct) {
+            rc = plan_enqueue(pl, mapped ? (void*)((char*)mapped + (gbase - base)) : (void*)gbase, format, false, true);
+        } else {
+            void* d = nullptr;
+            rc = grail_cuda_plan_device_output(pl, format, &d);
+            if (!rc) rc = plan_enqueue(pl, d, format, false, true);
+            if (!rc && pl->total_samples) {
+                cudaEvent_t ev = nullptr;
+                cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+                if (e == cudaSuccess) { done.push_back(ev); e = cudaEventRecord(ev, ctx->stream); }
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_copy, ev, 0);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(gbase, d, (size_t)pl->total_samples * eb, cudaMemcpyDeviceToHost, ctx->s_copy);
+                if (e != cudaSuccess) rc = set_err(ctx, GRAIL_ERR_CUDA, "device-to-host copy failed: %s", cudaGetErrorString(e));
+            }
+        }
     }
-    cudaStreamSynchronize(ctx->stream);
-    plan_release(pl);
+    // drain (also on the error paths: the plans' buffers go back to the pool)
+    cudaError_t es = cudaStreamSynchronize(ctx->stream);
+    cudaError_t ec = cudaStreamSynchronize(ctx->s_copy);
+    if (!rc && (es != cudaSuccess || ec != cudaSuccess))
+        rc = set_err(ctx, GRAIL_ERR_CUDA, "one-shot batch failed: %s", cudaGetErrorString(es != cudaSuccess ? es : ec));
+    for (grail_plan* pl : plans) {
+        if (!rc) rc = plan_check_device_errors(pl);
+        plan_release(pl);
+    }
+    for (cudaEvent_t ev : done) cudaEventDestroy(ev);
     return rc;
 }
 
@@ -1506,81 +1576,128 @@ int grail_cuda_stream_finish(grail_stream* s)
     return GRAIL_OK;
 }
 
+// The windows of n streams as ONE plan and one launch per kernel: utterance k of the plan is stream k's next window.
+// A server that runs many voices at once (examples/interactive.rs duplicates one stream over the output channels; a
+// speech service runs one per client) pays the launch and synchronisation latency once per tick, not once per stream.
+static int streams_pull_impl(grail_stream* const* streams, uint32_t n_streams, float* const* outs, const uint64_t* max_samples,
+                             uint64_t* n_written)
+{
+    grail_ctx* ctx = streams[0]->ctx;
+    std::vector<uint32_t> live;                  // streams that have something to synthesize in this call
+    for (uint32_t k = 0; k < n_streams; ++k) {
+        grail_stream* s = streams[k];
+        n_written[k] = 0;
+        if (s->ctx != ctx) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "streams of one call must share a ctx");
+        if (s->ended || max_samples[k] == 0 || s->pending.empty()) {
+            if (s->finished && s->pending.empty()) s->ended = true;
+            continue;
+        }
+        if (!s->finished && s->pending.size() < 2) continue;   // the only element is still just a look-ahead
+        if (!outs[k]) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "null output pointer");
+        live.push_back(k);
+    }
+    if (live.empty()) return GRAIL_OK;
+    const uint32_t nl = (uint32_t)live.size();
+    std::vector<grail_seq_elem> elems;
+    std::vector<uint32_t> offs(nl + 1, 0);
+    std::vector<grail_voice_params> voices(nl);
+    std::vector<StreamStart> ss(nl);
+    for (uint32_t i = 0; i < nl; ++i) {
+        grail_stream* s = streams[live[i]];
+        elems.insert(elems.end(), s->pending.begin(), s->pending.end());
+        offs[i + 1] = (uint32_t)elems.size();
+        voices[i] = s->voice;
+        ss[i] = s->st;
+        ss[i].filter_state = s->st.fresh ? nullptr : s->filter;
+        ss[i].max_samples = std::min<uint64_t>(max_samples[live[i]], MAX_UTT_SAMPLES);
+        ss[i].finished = s->finished;
+    }
+    grail_plan* pl = nullptr;
+    ElemInput in;
+    in.full = elems.data();
+    int rc = plan_build(ctx, in, offs.data(), voices.data(), nl, &pl, ss.data());
+    if (rc) return rc;
+    std::vector<float> fin((size_t)nl * 32, 0.0f);
+    if (pl->total_samples) {
+        void* d = nullptr;
+        rc = grail_cuda_plan_device_output(pl, GRAIL_F32, &d);
+        if (!rc) rc = plan_enqueue(pl, d, GRAIL_F32, false, true);
+        cudaError_t e = cudaSuccess;
+        if (!rc) e = cudaMemcpyAsync(fin.data(), pl->d_utt_final, fin.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+        for (uint32_t i = 0; i < nl && !rc && e == cudaSuccess; ++i) {
+            const uint64_t n = pl->utts[i].n_samples;
+            if (n) e = cudaMemcpyAsync(outs[live[i]], (const float*)d + pl->out_offsets[i], n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+        }
+        if (!rc && e != cudaSuccess) rc = set_err(ctx, GRAIL_ERR_CUDA, "stream read-back failed: %s", cudaGetErrorString(e));
+        if (!rc) rc = plan_check_device_errors(pl);             // synchronizes the stream
+        if (rc) {
+            cudaStreamSynchronize(ctx->stream);
+            plan_release(pl);
+            return rc;
+        }
+    }
+    // ---- every stream's iterator state after its last sample, from the exact host-side schedules
+    for (uint32_t i = 0; i < nl; ++i) {
+        grail_stream* s = streams[live[i]];
+        const UttDev& U = pl->utts[i];
+        const uint64_t n = U.n_samples;
+        if (n == 0) {
+            if (s->finished) { s->ended = true; s->pending.clear(); }
+            continue;
+        }
+        const SegRec* segs = pl->segs.data() + U.elem_first;
+        const float dt = sdiv(1.0f, s->voice.sample_rate);
+        const uint32_t last = (uint32_t)(n - 1);
+        uint32_t p = 0;
+        while (p + 1 < U.n_elems && segs[p + 1].start <= last) ++p;
+        const float time_last = clock_desc_run(segs[p].time0, dt, last - segs[p].start).x;
+        const JitSchedDev& js = pl->jscheds[U.jit_sched];
+        uint32_t w = 0;
+        while (w + 1 < js.n_recs && pl->jrecs[js.rec_first + w + 1].n <= (int32_t)last) ++w;
+        const JitRec& jr = pl->jrecs[js.rec_first + w];
+        const float* f = fin.data() + (size_t)i * 32;
+        StreamStart nx;
+        nx.fresh = false;
+        nx.jitter_phase = clock_asc_run(jr.phase, s->voice.jitter_frequency, (uint64_t)((int64_t)last - jr.n)).x;
+        nx.jitter_wraps = s->st.jitter_wraps + w;
+        nx.sample0 = s->st.sample0 + n;
+        nx.carrier_phase = f[24];
+        memcpy(s->filter, f, sizeof s->filter);
+        // Sequencer: what the next call to next() will do with `time` (src/lib.rs:861-888)
+        const float t_next = ssub(time_last, dt);
+        uint32_t consumed;
+        if (t_next < 0.0f) {            // the hand-over happens on the next sample: phoneme p is done
+            nx.cont_phoneme = false;
+            nx.t_neg = t_next;
+            consumed = p + 1;
+        } else {                        // phoneme p continues
+            nx.cont_phoneme = true;
+            nx.time0 = t_next;
+            consumed = p;
+        }
+        s->pending.erase(s->pending.begin(), s->pending.begin() + consumed);
+        s->st = nx;
+        if (s->finished && s->pending.empty()) s->ended = true;
+        n_written[live[i]] = n;
+    }
+    plan_release(pl);
+    return GRAIL_OK;
+}
+
 int grail_cuda_stream_pull(grail_stream* s, float* out, uint64_t max_samples, uint64_t* n_written)
 {
     if (!s || !n_written || (max_samples && !out)) return GRAIL_ERR_INVALID_ARG;
-    *n_written = 0;
-    grail_ctx* ctx = s->ctx;
-    if (s->ended || max_samples == 0 || s->pending.empty()) {
-        if (s->finished && s->pending.empty()) s->ended = true;
-        return GRAIL_OK;
-    }
-    if (!s->finished && s->pending.size() < 2) return GRAIL_OK;   // the only element is still just a look-ahead
-    StreamStart ss = s->st;
-    ss.filter_state = s->st.fresh ? nullptr : s->filter;
-    ss.max_samples = std::min<uint64_t>(max_samples, MAX_UTT_SAMPLES);
-    ss.finished = s->finished;
-    const uint32_t offs[2] = { 0u, (uint32_t)s->pending.size() };
-    grail_plan* pl = nullptr;
-    ElemInput in;
-    in.full = s->pending.data();
-    int rc = plan_build(ctx, in, offs, &s->voice, 1, &pl, &ss);
-    if (rc) return rc;
-    const uint64_t n = pl->total_samples;
-    if (n == 0) {
-        plan_release(pl);
-        if (s->finished) { s->ended = true; s->pending.clear(); }
-        return GRAIL_OK;
-    }
-    void* d = nullptr;
-    rc = grail_cuda_plan_device_output(pl, GRAIL_F32, &d);
-    if (!rc) rc = plan_enqueue(pl, d, GRAIL_F32, false, true);
-    float fin[32];
-    if (!rc) {
-        cudaError_t e = cudaMemcpyAsync(fin, pl->d_utt_final, sizeof fin, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e != cudaSuccess) rc = set_err(ctx, GRAIL_ERR_CUDA, "state read-back failed: %s", cudaGetErrorString(e));
-    }
-    if (!rc) rc = grail_cuda_plan_read_output(pl, GRAIL_F32, out);    // synchronizes the stream
-    if (rc) {
-        cudaStreamSynchronize(ctx->stream);
-        plan_release(pl);
-        return rc;
-    }
-    // ---- the iterators' state after sample n-1, from the exact host-side schedules
-    const float dt = sdiv(1.0f, s->voice.sample_rate);
-    const uint32_t last = (uint32_t)(n - 1);
-    uint32_t p = 0;
-    while (p + 1 < pl->utts[0].n_elems && pl->segs[p + 1].start <= last) ++p;
-    const float time_last = clock_desc_run(pl->segs[p].time0, dt, last - pl->segs[p].start).x;
-    const JitSchedDev& js = pl->jscheds[0];
-    uint32_t w = 0;
-    while (w + 1 < js.n_recs && pl->jrecs[js.rec_first + w + 1].n <= (int32_t)last) ++w;
-    const JitRec& jr = pl->jrecs[js.rec_first + w];
-    StreamStart nx;
-    nx.fresh = false;
-    nx.jitter_phase = clock_asc_run(jr.phase, s->voice.jitter_frequency, (uint64_t)((int64_t)last - jr.n)).x;
-    nx.jitter_wraps = s->st.jitter_wraps + w;
-    nx.sample0 = s->st.sample0 + n;
-    nx.carrier_phase = fin[24];
-    memcpy(s->filter, fin, sizeof s->filter);
-    // Sequencer: what the next call to next() will do with `time` (src/lib.rs:861-888)
-    const float t_next = ssub(time_last, dt);
-    uint32_t consumed;
-    if (t_next < 0.0f) {            // the hand-over happens on the next sample: phoneme p is done
-        nx.cont_phoneme = false;
-        nx.t_neg = t_next;
-        consumed = p + 1;
-    } else {                        // phoneme p continues
-        nx.cont_phoneme = true;
-        nx.time0 = t_next;
-        consumed = p;
-    }
-    s->pending.erase(s->pending.begin(), s->pending.begin() + consumed);
-    s->st = nx;
-    if (s->finished && s->pending.empty()) s->ended = true;
-    plan_release(pl);
-    *n_written = n;
-    return GRAIL_OK;
+    return streams_pull_impl(&s, 1, &out, &max_samples, n_written);
+}
+
+int grail_cuda_streams_pull(grail_stream* const* streams, uint32_t n_streams, float* const* outs, const uint64_t* max_samples,
+                            uint64_t* n_written)
+{
+    if (n_streams == 0) return GRAIL_OK;
+    if (!streams || !outs || !max_samples || !n_written) return GRAIL_ERR_INVALID_ARG;
+    for (uint32_t k = 0; k < n_streams; ++k)
+        if (!streams[k]) return GRAIL_ERR_INVALID_ARG;
+    return streams_pull_impl(streams, n_streams, outs, max_samples, n_written);
 }
 
 void grail_cuda_stream_free(grail_stream* s) { delete s; }

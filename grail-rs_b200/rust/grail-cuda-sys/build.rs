@@ -20,11 +20,13 @@ fn main() {
         .flag("-Xcompiler")
         .flag("-ffp-contract=off")
         .file(csrc.join("grail_runtime.cu"))
+        .file(csrc.join("grail_text.cpp"))          // grail_cuda_transcribe_batch
         .compile("grail_cuda");
     let bindings = bindgen::Builder::default()
         .header(root.join("include/grail_cuda.h").to_str().unwrap())
         .allowlist_function("grail_cuda_.*")
         .allowlist_type("grail_.*")
+        .prepend_enum_name(false)                   // GRAIL_F32, not grail_sample_format_GRAIL_F32
         .generate()
         .expect("bindgen failed");
     bindings

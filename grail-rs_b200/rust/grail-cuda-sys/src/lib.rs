@@ -17,6 +17,8 @@ impl Ctx {
 
     /// exact per-utterance sample counts (host only)
     pub fn count_samples(elems: &[grail_seq_elem], utt_offsets: &[u32], voices: &[grail_voice_params]) -> Result<Vec<u64>, i32> {
+        assert_eq!(utt_offsets.len(), voices.len() + 1, "utt_offsets has one entry more than there are utterances");
+        assert!(utt_offsets.windows(2).all(|w| w[0] <= w[1]) && *utt_offsets.last().unwrap() as usize <= elems.len());
         let n = voices.len() as u32;
         let mut counts = vec![0u64; voices.len()];
         match unsafe { grail_cuda_count_samples(elems.as_ptr(), utt_offsets.as_ptr(), voices.as_ptr(), n, counts.as_mut_ptr()) } {
@@ -28,6 +30,7 @@ impl Ctx {
     /// drains the whole batch into `out` (packed, utterance `u` at `out_offsets[u]`)
     pub fn synthesize_batch(&mut self, elems: &[grail_seq_elem], utt_offsets: &[u32], voices: &[grail_voice_params],
                             out: &mut [f32], out_offsets: &[u64]) -> Result<(), i32> {
+        check_batch_slices(elems.len(), utt_offsets, voices.len(), out.len(), out_offsets);
         let rc = unsafe {
             grail_cuda_synthesize_batch(self.0, elems.as_ptr(), utt_offsets.as_ptr(), voices.as_ptr(), voices.len() as u32,
                                         out.as_mut_ptr(), out_offsets.as_ptr(), 0)
@@ -41,6 +44,7 @@ impl Ctx {
     /// (`(x * i16::MAX as f32) as i16`, examples/cli.rs:49-51): half the device-to-host bytes.
     pub fn synthesize_batch_i16(&mut self, elems: &[grail_seq_elem], utt_offsets: &[u32], voices: &[grail_voice_params],
                                 out: &mut [i16], out_offsets: &[u64]) -> Result<(), i32> {
+        check_batch_slices(elems.len(), utt_offsets, voices.len(), out.len(), out_offsets);
         let rc = unsafe {
             grail_cuda_synthesize_batch_i16(self.0, elems.as_ptr(), utt_offsets.as_ptr(), voices.as_ptr(), voices.len() as u32,
                                             out.as_mut_ptr(), out_offsets.as_ptr(), 0)
@@ -48,6 +52,42 @@ impl Ctx {
         if rc == 0 { Ok(()) } else { Err(rc) }
     }
 }
+
+/// the slice invariants the C side relies on (safe Rust must not be able to make C read or write out of bounds)
+fn check_batch_slices(n_elems: usize, utt_offsets: &[u32], n_utts: usize, out_len: usize, out_offsets: &[u64]) {
+    assert_eq!(utt_offsets.len(), n_utts + 1);
+    assert_eq!(out_offsets.len(), n_utts + 1);
+    assert!(utt_offsets.windows(2).all(|w| w[0] <= w[1]) && *utt_offsets.last().unwrap() as usize <= n_elems);
+    assert!(out_offsets.windows(2).all(|w| w[0] <= w[1]) && *out_offsets.last().unwrap() as usize <= out_len);
+}
+
+/// One unbounded utterance with carried iterator state (`grail_stream`): what the facade's lazy `Synthesize` pulls from.
+pub struct Stream(*mut grail_stream);
+// the handle is used from one thread at a time and may move to the audio thread (examples/interactive.rs moves the iterator)
+unsafe impl Send for Stream {}
+
+impl Stream {
+    pub fn new(ctx: &Ctx, voice: &grail_voice_params) -> Result<Self, i32> {
+        let mut p = std::ptr::null_mut();
+        match unsafe { grail_cuda_stream_new(ctx.0, voice, &mut p) } { 0 => Ok(Stream(p)), e => Err(e) }
+    }
+    pub fn push(&mut self, elems: &[grail_seq_elem]) -> Result<(), i32> {
+        match unsafe { grail_cuda_stream_push(self.0, elems.as_ptr(), elems.len() as u32) } { 0 => Ok(()), e => Err(e) }
+    }
+    pub fn finish(&mut self) -> Result<(), i32> {
+        match unsafe { grail_cuda_stream_finish(self.0) } { 0 => Ok(()), e => Err(e) }
+    }
+    /// up to `out.len()` more samples; returns how many were written (0: the upstream has run dry)
+    pub fn pull(&mut self, out: &mut [f32]) -> Result<usize, i32> {
+        let mut n = 0u64;
+        match unsafe { grail_cuda_stream_pull(self.0, out.as_mut_ptr(), out.len() as u64, &mut n) } { 0 => Ok(n as usize), e => Err(e) }
+    }
+}
+impl Drop for Stream {
+    fn drop(&mut self) { unsafe { grail_cuda_stream_free(self.0) } }
+}
+unsafe impl Send for Ctx {}
+unsafe impl Sync for Ctx {}   // the C side serialises nothing: the facade keeps its shared Ctx behind a Mutex
 
 /// The reference's `Transcriber` (src/lib.rs:1098-1207) over a batch of texts on all host cores (host only).
 /// `rules` must be sorted by string; returns (phoneme ids, utterance offsets) in the layout `Plan::from_phonemes` takes.
@@ -74,6 +114,8 @@ pub struct Plan(*mut grail_plan);
 impl Plan {
     /// Sequencer records in (the path's own boundary).
     pub fn new(ctx: &mut Ctx, elems: &[grail_seq_elem], utt_offsets: &[u32], voices: &[grail_voice_params]) -> Result<Self, i32> {
+        assert_eq!(utt_offsets.len(), voices.len() + 1);
+        assert!(utt_offsets.windows(2).all(|w| w[0] <= w[1]) && *utt_offsets.last().unwrap() as usize <= elems.len());
         let mut p = std::ptr::null_mut();
         match unsafe { grail_cuda_plan_create(ctx.0, elems.as_ptr(), utt_offsets.as_ptr(), voices.as_ptr(), voices.len() as u32, &mut p) } {
             0 => Ok(Plan(p)),

@@ -383,6 +383,22 @@ class Stream:
             self._L.grail_cuda_stream_free(self._h)
             self._h = None
 
+
+def pull_streams(streams, max_samples) -> list:
+    """the next windows of several streams of one Context as one launch per kernel (grail_cuda_streams_pull); returns
+    one array per stream"""
+    if not streams:
+        return []
+    n = len(streams)
+    ms = np.ascontiguousarray(np.broadcast_to(np.asarray(max_samples, np.uint64), (n,)))
+    outs = [np.empty(int(m), np.float32) for m in ms]
+    hs = (C.c_void_p * n)(*[s._h for s in streams])
+    ps = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+    wr = np.zeros(n, np.uint64)
+    ctx = streams[0].ctx
+    ctx._check(ctx._L.grail_cuda_streams_pull(hs, n, ps, ptr(ms), ptr(wr)))
+    return [o[: int(w)] for o, w in zip(outs, wr)]
+
     __del__ = close
 
 

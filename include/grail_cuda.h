@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 #define GRAIL_NUM_FORMANTS 8 /* reference NUM_FORMANTS, src/lib.rs:24 */
-#define GRAIL_ABI_VERSION 4   /* 2: phoneme-level plans, grail_cuda_transcribe_batch; 3: grail_cuda_plan_phase_stats; 4: grail_cuda_copy_segments */
+#define GRAIL_ABI_VERSION 4   /* 2: phoneme-level plans, grail_cuda_transcribe_batch; 3: grail_cuda_plan_phase_stats; 4: grail_cuda_copy_segments, grail_cuda_streams_pull */
 
 typedef enum grail_status {
     GRAIL_OK = 0,
@@ -113,7 +113,8 @@ void* grail_cuda_stream_handle(grail_ctx* ctx);
 int  grail_cuda_synchronize(grail_ctx* ctx);
 /* tuning knobs: "warmup_nepers" (float, filter warm-up depth, default 13.8 ~ 1e-6),
  * "target_lanes" (int, time-chunks the planner aims for), "max_chunk" / "min_chunk" (samples),
- * "formants_per_lane" (1|2), "pipeline" (0|1: overlap consecutive launches of a plan), "pscan_min_samples",
+ * "formants_per_lane" (1|2), "pipeline" (0|1: overlap consecutive launches of a plan), "e2e_groups", "phase_mode",
+ * "phase_chunk", "phase_rounds" (see grail_cuda_plan_phase_stats), "pscan_min_samples",
  * "pscan_cost_model" (0|1), "zero_copy_out" (0|1), "interleave" (0|1: interleave equally long utterances chunk by
  * chunk in the formant kernel's CTAs), "phase_lean" (-1 auto | 0 | 1: which build of the phase kernel) */
 int  grail_cuda_set_option(grail_ctx* ctx, const char* key, double value);
@@ -153,7 +154,9 @@ int grail_cuda_transcribe_batch(const char* const* texts, const size_t* text_byt
  * elems / utt_offsets / voices are HOST pointers.  out receives utterance u at
  * out[out_offsets[u] .. out_offsets[u+1]) (mono f32); out_offsets[u+1]-out_offsets[u] must equal
  * the exact count, else GRAIL_ERR_COUNT_MISMATCH.  out is a host pointer (pinned or pageable)
- * unless out_is_device != 0.  Blocks until the samples are in `out`. */
+ * unless out_is_device != 0.  Blocks until the samples are in `out`.  With a host `out` the batch is processed as a
+ * few utterance groups of growing size whose device-to-host copies overlap the next group's kernels (ctx option
+ * "e2e_groups": -1 auto, 1 = one plan and one copy); the samples are the same to rounding level either way. */
 int grail_cuda_synthesize_batch(grail_ctx* ctx, const grail_seq_elem* elems, const uint32_t* utt_offsets,
                                 const grail_voice_params* voices, uint32_t n_utts, float* out,
                                 const uint64_t* out_offsets, int out_is_device);
@@ -195,15 +198,16 @@ int  grail_cuda_plan_launch(grail_plan* plan, void* d_out, int format);
  * `flat_map(|x| repeat(x).take(num_channels))` (examples/cli.rs:229, interactive.rs:38) done on the device.
  * d_out holds total_samples * channels elements; utterance u starts at out_offsets[u] * channels. */
 int  grail_cuda_plan_launch_interleaved(grail_plan* plan, void* d_out, int format, uint32_t channels);
-/* With ctx option "pipeline" = 1 (off by default: measured no gain on B200, the latency-bound phase chains starve
- * when they share SM sub-partitions with the formant kernel) launches of one plan are pipelined across the library's
- * internal streams.  grail_cuda_plan_join makes the ctx's main stream (grail_cuda_stream_handle) wait, on the device,
+/* With ctx option "pipeline" = 1 at plan creation (off by default, so that launches complete in stream order without
+ * a join) consecutive launches of one plan are pipelined across the library's internal streams: launch k+1's
+ * frequency / phase kernels run on a second scratch set under launch k's filter kernel (+4 % at config 2, same bits).  grail_cuda_plan_join makes the ctx's main stream (grail_cuda_stream_handle) wait, on the device,
  * for everything the plan has in flight -- call it before recording an event or enqueueing a consumer on that stream
  * (a no-op for unpipelined plans).  grail_cuda_synchronize, plan_read_output and plan_timings join implicitly. */
 int  grail_cuda_plan_join(grail_plan* plan);
 /* the plan's own device output buffer (allocated on first use), for callers with no allocator */
 int  grail_cuda_plan_device_output(grail_plan* plan, int format, void** out_dptr);
-/* D2H of the packed output into a host buffer (chunked, through pinned staging if pageable) */
+/* D2H of the packed output into a host buffer (one cudaMemcpyAsync on the ctx stream, then a synchronize; pinned host
+ * memory -- grail_cuda_host_alloc -- gets the full PCIe rate) */
 int  grail_cuda_plan_read_output(grail_plan* plan, int format, void* host_out);
 int  grail_cuda_plan_timings(const grail_plan* plan, grail_timings* out);
 /* Long utterances (>= option "pscan_min_samples", "pscan_cost_model" (0|1), default 2^18) may get their carrier phase from the exact parallel
@@ -240,6 +244,11 @@ int  grail_cuda_stream_new(grail_ctx* ctx, const grail_voice_params* voice, grai
 int  grail_cuda_stream_push(grail_stream* s, const grail_seq_elem* elems, uint32_t n_elems);
 int  grail_cuda_stream_finish(grail_stream* s);
 int  grail_cuda_stream_pull(grail_stream* s, float* out, uint64_t max_samples, uint64_t* n_written);
+/* the next windows of n_streams streams of one ctx as ONE plan and one launch per kernel (a server's tick): the same
+ * result per stream as n_streams separate pulls, for one launch / synchronisation latency instead of n_streams.
+ * outs[k] receives up to max_samples[k] samples of streams[k]; n_written[k] how many it got. */
+int  grail_cuda_streams_pull(grail_stream* const* streams, uint32_t n_streams, float* const* outs, const uint64_t* max_samples,
+                             uint64_t* n_written);
 void grail_cuda_stream_free(grail_stream* s);
 
 /* ---- multi-GPU output gather helper ("optional gather of outputs to one rank") ----------------------------

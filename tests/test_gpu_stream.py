@@ -90,3 +90,32 @@ def test_stream_multi_chunk_window_narrow_bandwidth(ctx, oracle):
     print(stats)
     assert stats["max_abs"] <= 1e-4 and stats["snr_db"] >= 90.0, stats
     st.close()
+
+
+def test_batched_streams_pull_equals_separate_streams(ctx, oracle):
+    """grail_cuda_streams_pull: the windows of several concurrent streams (different voices, seeds, lengths, one of
+    them running dry early) as one launch per kernel; every stream equals its one-shot result"""
+    v = g.voices.generic()
+    lists = [[0, 3, 4, 3], [4, 3], [0, 0, 3, 4, 4, 3], [3]]
+    elems, offs, vp = W.from_phonemes(lists, v, [1, 2, 3, 4])
+    e4, o4, v4 = W.config4(2, first_utt=77)                       # two random-voice streams next to the default voice
+    streams, wants = [], []
+    for u in range(4):
+        st = ctx.stream(vp[u]); st.push(elems[offs[u]:offs[u + 1]]); st.finish()
+        streams.append(st); wants.append(oracle.synthesize(elems[offs[u]:offs[u + 1]], vp[u])[0])
+    for u in range(2):
+        st = ctx.stream(v4[u]); st.push(e4[o4[u]:o4[u + 1]]); st.finish()
+        streams.append(st); wants.append(oracle.synthesize(e4[o4[u]:o4[u + 1]], v4[u])[0])
+    got = [[] for _ in streams]
+    for tick in range(10000):
+        xs = g.pull_streams(streams, [3000, 4410, 777, 5000, 2048, 9999])
+        if all(len(x) == 0 for x in xs):
+            break
+        for k, x in enumerate(xs):
+            got[k].append(x.copy())
+    for k, st in enumerate(streams):
+        y = np.concatenate(got[k])
+        assert len(y) == len(wants[k]), k
+        stats = W.parity_stats(y, wants[k])
+        assert stats["max_abs"] <= 1e-4 and stats["snr_db"] >= 90.0, (k, stats)
+        st.close()
