@@ -1233,6 +1233,13 @@ struct FormantLane {
     int fi;                 // formant index, -1 if this slot is unused
 };
 
+// samples between two CTA-wide reductions of the partial sums (a power of two, at least 32)
+#ifndef KF_TILE
+#define KF_TILE 32
+#endif
+#ifndef KF_ALG2
+#define KF_ALG2 0
+#endif
 template <int FPT> struct FormantCfg { static constexpr int warps_per_sm = 24; };   // 80 registers per lane
 template <> struct FormantCfg<2> { static constexpr int warps_per_sm = 12; };       // up to 168 registers per lane
 
@@ -1242,7 +1249,9 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
 {
     // partial sums: [formant group][chunk row][32 samples], rows padded to 36 floats so that both the per-lane
     // 128-bit row writes and the 8-lanes-per-row 128-bit reads of the reduction are bank-conflict free
-    __shared__ __align__(16) float part[NW][32][36];
+    // (static shared memory ends at 48 KB: instantiations with many formant groups fall back to 32-sample tiles)
+    constexpr int KT = (NW * 32 * (KF_TILE + 4) * 4 + 1024 <= 49152) ? KF_TILE : 32;
+    __shared__ __align__(16) float part[NW][32][KT + 4];
     __shared__ unsigned long long row_out[32];
     __shared__ uint32_t row_len[32];
 
@@ -1460,7 +1469,7 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
     uint32_t lmax = 0;
 #pragma unroll 1
     for (int r = 0; r < 32; ++r) lmax = max(lmax, row_len[r]);
-    lmax = (lmax + 31u) & ~31u;      // whole 32-sample batches: the reduction runs at the end of each
+    lmax = (lmax + (uint32_t)(KT - 1)) & ~(uint32_t)(KT - 1);      // whole KT-sample batches: the reduction runs at the end of each
 
     // saw source: walks the tiled layout from sample ns; crossing into the next chunk of the utterance (and,
     // at r == 0, into this lane's own chunk) is a pointer reset every CL samples
@@ -1506,8 +1515,8 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
     Coef c0[FPT], dc[FPT];
 #pragma unroll
     for (int j = 0; j < FPT; ++j) { c0[j] = cend[j]; dc[j] = cend[j]; }
-    struct Coef2 { f2_t a1, g, lp, amp0, amp1, br; };
-    Coef2 p0 = { 0ull, 0ull, 0ull, 0ull, 0ull, 0ull }, pd = p0;   // packed block start / block delta (FPT = 2)
+    struct Coef2 { f2_t a1, g, lp, amp0, amp1, br, m1; };
+    Coef2 p0 = { 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull }, pd = p0;   // packed block start / block delta (FPT = 2)
     bool hand = false, warp_exact = false;
     int half = 0;
     for (int r = -(int)wmax; r < (int)lmax; r += 8, half ^= 1) {
@@ -1598,9 +1607,17 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
 #pragma unroll
                         for (int j = 0; j < FPT; ++j) cend[j] = coeffs(L[j], alpha, jph);
                         const Coef e0 = cend[0], e1 = cend[FPT - 1];
+#if KF_ALG2
+                        p0.a1 = pk(s0.a1, s1.a1); p0.g = pk(2.0f * s0.g, 2.0f * s1.g); p0.lp = pk(s0.lp, s1.lp);
+                        p0.m1 = pk(s0.a1 * s0.g, s1.a1 * s1.g);
+                        pd.m1 = sub2(pk(e0.a1 * e0.g, e1.a1 * e1.g), p0.m1);
+                        p0.amp0 = pk(s0.amp0, s1.amp0); p0.amp1 = pk(s0.amp1, s1.amp1); p0.br = pk(s0.br, s1.br);
+                        pd.a1 = sub2(pk(e0.a1, e1.a1), p0.a1); pd.g = sub2(pk(2.0f * e0.g, 2.0f * e1.g), p0.g);
+#else
                         p0.a1 = pk(s0.a1, s1.a1); p0.g = pk(s0.g, s1.g); p0.lp = pk(s0.lp, s1.lp);
                         p0.amp0 = pk(s0.amp0, s1.amp0); p0.amp1 = pk(s0.amp1, s1.amp1); p0.br = pk(s0.br, s1.br);
                         pd.a1 = sub2(pk(e0.a1, e1.a1), p0.a1); pd.g = sub2(pk(e0.g, e1.g), p0.g);
+#endif
                         pd.lp = sub2(pk(e0.lp, e1.lp), p0.lp); pd.amp0 = sub2(pk(e0.amp0, e1.amp0), p0.amp0);
                         pd.amp1 = sub2(pk(e0.amp1, e1.amp1), p0.amp1); pd.br = sub2(pk(e0.br, e1.br), p0.br);
                         c_valid = true;
@@ -1608,6 +1625,9 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
                         const f2_t hf = pk(0.5f, 0.5f);                 // second half: start from the block's midpoint
                         p0.a1 = fma2(pd.a1, hf, p0.a1); p0.g = fma2(pd.g, hf, p0.g); p0.lp = fma2(pd.lp, hf, p0.lp);
                         p0.amp0 = fma2(pd.amp0, hf, p0.amp0); p0.amp1 = fma2(pd.amp1, hf, p0.amp1); p0.br = fma2(pd.br, hf, p0.br);
+#if KF_ALG2
+                        p0.m1 = fma2(pd.m1, hf, p0.m1);
+#endif
                     }
                     f2_t A = pk(L[0].a, L[FPT - 1].a), B = pk(L[0].b, L[FPT - 1].b), Cc = pk(L[0].c, L[FPT - 1].c);
 #pragma unroll
@@ -1616,6 +1636,18 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
                         noise(s8[k], d1, nz);
                         const float tk = (float)k * 0.0625f;
                         const f2_t t = pk(tk, tk), saw2 = pk(s8[k], s8[k]), d2 = pk(d1, d1), n2 = pk(nz, nz);
+#if KF_ALG2
+                        // (p0.g / pd.g hold 2 g and p0.m1 / pd.m1 hold a1 g here: one product and one sum fewer per sample)
+                        const f2_t a1 = fma2(pd.a1, t, p0.a1), g2 = fma2(pd.g, t, p0.g), m1 = fma2(pd.m1, t, p0.m1), lp = fma2(pd.lp, t, p0.lp);
+                        const f2_t amp0 = fma2(pd.amp0, t, p0.amp0), amp1 = fma2(pd.amp1, t, p0.amp1), br = fma2(pd.br, t, p0.br);
+                        const f2_t nw = fma2(br, d2, saw2);                              // :531
+                        A = fma2(lp, sub2(nw, A), A);                                    // :538
+                        const f2_t v0 = mul2(A, fma2(amp1, n2, amp0));                   // :544-550
+                        const f2_t v3 = sub2(v0, Cc);                                    // :565
+                        const f2_t v1 = fma2(m1, v3, mul2(a1, B));                       // a1 b + a2 v3   (:566)
+                        Cc = fma2(g2, v1, Cc);                                           // 2 v2 - c = c + 2 g v1
+                        B = sub2(mul2(v1, pk(2.0f, 2.0f)), B);                           // 2 v1 - b (one FFMA2 with a negated addend)
+#else
                         const f2_t a1 = fma2(pd.a1, t, p0.a1), g = fma2(pd.g, t, p0.g), lp = fma2(pd.lp, t, p0.lp);
                         const f2_t amp0 = fma2(pd.amp0, t, p0.amp0), amp1 = fma2(pd.amp1, t, p0.amp1), br = fma2(pd.br, t, p0.br);
                         const f2_t nw = fma2(br, d2, saw2);                              // :531
@@ -1628,6 +1660,7 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
                         const f2_t v1 = fma2(mul2(a1, g), v3, mul2(a1, B));
                         Cc = fma2(add2(g, g), v1, Cc);
                         B = sub2(add2(v1, v1), B);
+#endif
                         float x0, x1;
                         unpk(v1, x0, x1);
                         v[k] = x0 + x1;
@@ -1664,10 +1697,10 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
                     if (time < 0.0f) handover();                             // :864
                     jph = __fadd_rn(jph, jinc);
                     if (jph > 1.0f) jitter_wrap();
-                    sts32(part_a + ((r & 31) + k) * 4, vk);
+                    sts32(part_a + ((r & (KT - 1)) + k) * 4, vk);
                 }
                 if (r >= 0) {
-                    const float4 t0 = lds128(part_a + (r & 31) * 4), t1 = lds128(part_a + (r & 31) * 4 + 16);
+                    const float4 t0 = lds128(part_a + (r & (KT - 1)) * 4), t1 = lds128(part_a + (r & (KT - 1)) * 4 + 16);
                     v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w;
                     v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
                 }
@@ -1677,23 +1710,24 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
             for (int k = 0; k < 8; ++k) v[k] = 0.0f;
         }
         if (r >= 0) {
-            sts128(part_a + (r & 31) * 4, v[0], v[1], v[2], v[3]);
-            sts128(part_a + (r & 31) * 4 + 16, v[4], v[5], v[6], v[7]);
-            if ((r & 31) == 24) {
-                const uint32_t base = (uint32_t)r - 24u;
+            sts128(part_a + (r & (KT - 1)) * 4, v[0], v[1], v[2], v[3]);
+            sts128(part_a + (r & (KT - 1)) * 4 + 16, v[4], v[5], v[6], v[7]);
+            if ((r & (KT - 1)) == KT - 8) {
+                const uint32_t base = (uint32_t)r - (uint32_t)(KT - 8);
                 __syncthreads();
                 // 8 lanes per row, 4 rows per pass: sum the formant groups in index order (Array::sum, :123),
                 // scale (:574), store 16 bytes per lane = 128 contiguous bytes per row
                 const int sub = lane >> 3, l8 = lane & 7;
 #pragma unroll 1
-                for (int row = w * 4 + sub; row < 32; row += NW * 4) {
+                for (int rc = w * 4 + sub; rc < 32 * (KT / 32); rc += NW * 4) {
+                    const int row = rc & 31, cb = (rc >> 5) * 32;          // (row, 32-sample column block) of the tile
                     const uint32_t rl = row_len[row];
-                    const uint32_t s0 = base + l8 * 4;
+                    const uint32_t s0 = base + cb + l8 * 4;
                     if (s0 < rl) {
-                        float4 acc = *reinterpret_cast<const float4*>(&part[0][row][l8 * 4]);
+                        float4 acc = *reinterpret_cast<const float4*>(&part[0][row][cb + l8 * 4]);
 #pragma unroll
                         for (int f = 1; f < NW; ++f) {
-                            const float4 t = *reinterpret_cast<const float4*>(&part[f][row][l8 * 4]);
+                            const float4 t = *reinterpret_cast<const float4*>(&part[f][row][cb + l8 * 4]);
                             acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
                         }
                         acc.x *= 0.5f; acc.y *= 0.5f; acc.z *= 0.5f; acc.w *= 0.5f;

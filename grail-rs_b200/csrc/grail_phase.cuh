@@ -30,7 +30,7 @@
 // warp of the walks is the same sub-range of 32 work items of one k_formant group: lane l reads 32 bytes of item l per
 // 8-sample block, the warp 1 KB of consecutive addresses, and round B stores the saw to the very same offsets.  Both
 // rounds are plain streaming kernels bound by HBM (round A reads F_t about 1.2 times, round B reads it once and
-// writes the saw once); the loads run four blocks ahead of the arithmetic in registers.
+// writes the saw once); the loads run eight blocks ahead of the arithmetic through a cp.async ring in shared memory.
 // (First version, kept in profiles/r2_phase_strided_launches.csv: linear F_t, one lane per CONSECUTIVE chunk of an
 //  utterance, i.e. 32 lanes reading 32 places 8 KB apart -- per-lane 128-byte TMA bulk copies (cp.async.bulk +
 //  mbarrier complete_tx) into private shared-memory rows as well as LDG.256 / 16-byte cp.async all ended at 0.84 ms
@@ -64,6 +64,7 @@ enum { PSTAT_WALKS = 0,       // chunks walked by k_phase_b, all rounds
        PSTAT_PENDING = 16 };  // + r: dirty chunks waiting for round r's k_phase_b
 
 constexpr int PH_MAX_ROUNDS = 14;
+constexpr int PH_OCC = 6;      // CTAs of 128 lanes per SM the walks are compiled for (<= 85 registers, 32 KB of ring each)
 constexpr float PH_U23 = 1.1920928955078125e-07f;   // 2^-23
 
 __device__ __forceinline__ float* pcf(const PlanDev& P, int field) { return P.pchunks + (size_t)field * P.pc_stride; }
@@ -168,41 +169,57 @@ struct TileCursor {
 };
 
 // fn(blk, off, f) for every 8-sample block of [t0, t1) (both multiples of 8) in order; `off` is the block's offset in
-// the tiled arrays; fn returns false to stop early.  Loads run four blocks ahead (32 registers).
+// the tiled arrays; fn returns false to stop early.
+// The stream runs through a per-lane ring of PH_DEPTH 32-byte slots in shared memory filled with cp.async (LDGSTS):
+// groups complete in order, so `wait_group PH_DEPTH-1` is an exact, per-lane "block i has landed" with PH_DEPTH-1 more
+// blocks in flight behind it.  (First version: the next four blocks in registers, LDG.256 -- ncu showed the walks
+// parked on the register copies of three of the four ring slots, long_scoreboard 7.6 per issue: ptxas folds the ring's
+// loads onto shared scoreboard entries, which turns "four blocks ahead" into "one block ahead", 1 450 cycles per block.)
+// Slots are private to their lane (no synchronisation, lanes may diverge and stop at different blocks); the two
+// 16-byte halves of a slot are swapped for every other group of four lanes so that the 128-bit reads of a warp fall
+// on all 32 banks.
+constexpr int PH_DEPTH = 8;
+constexpr unsigned PH_STAGE_BYTES = 128u * 32u;             // one block of every lane of the CTA
+constexpr unsigned PH_RING_BYTES = PH_DEPTH * PH_STAGE_BYTES;
+
 template <class Fn>
-__device__ __forceinline__ void walk_blocks(const float* __restrict__ F, const UttDev& U, uint32_t CL, uint32_t t0, uint32_t t1,
-                                            Fn&& fn)
+__device__ __forceinline__ void walk_blocks(unsigned char* ring, const float* __restrict__ F, const UttDev& U, uint32_t CL,
+                                            uint32_t t0, uint32_t t1, Fn&& fn)
 {
     if (t0 >= t1) return;
     TileCursor ld, cur;
     ld.seek(U, t0, CL);
     cur = ld;
-    uint32_t tl = t0;
-    float r0[8], r1[8], r2[8], r3[8];
-#define PH_FETCH(R)                                   \
-    do {                                              \
-        if (tl < t1) { ldg256(F + ld.off, R); ld.next(); tl += 8u; } \
-    } while (0)
-    PH_FETCH(r0); PH_FETCH(r1); PH_FETCH(r2); PH_FETCH(r3);
-    uint32_t blk = t0;
-    bool go = true;
-#define PH_USE(R)                                     \
-    do {                                              \
-        if (go && blk < t1) {                         \
-            float f_[8];                              \
-            _Pragma("unroll") for (int k_ = 0; k_ < 8; ++k_) f_[k_] = R[k_]; \
-            PH_FETCH(R);                              \
-            go = fn(blk, cur.off, f_);                \
-            cur.next();                               \
-            blk += 8u;                                \
-        }                                             \
-    } while (0)
+    const unsigned swz = ((threadIdx.x >> 2) & 1u) << 4;
+    const unsigned slot = (unsigned)__cvta_generic_to_shared(ring) + threadIdx.x * 32u;
+    uint32_t tl = t0, is = 0;                       // next block to load and its stage
+    auto issue = [&]() {
+        if (tl < t1) {
+            const unsigned a = slot + is * PH_STAGE_BYTES;
+            cp_async16(a + swz, F + ld.off);
+            cp_async16(a + (swz ^ 16u), F + ld.off + 4);
+            ld.next();
+            tl += 8u;
+        }
+        cp_async_commit();                          // (an empty group when the stream is over: the count stays uniform)
+        is = (is + 1u) & (PH_DEPTH - 1u);
+    };
+#pragma unroll
+    for (int i = 0; i < PH_DEPTH - 1; ++i) issue();
+    uint32_t cs = 0;
 #pragma unroll 1
-    while (go && blk < t1) {
-        PH_USE(r0); PH_USE(r1); PH_USE(r2); PH_USE(r3);
+    for (uint32_t blk = t0; blk < t1; blk += 8u) {
+        issue();
+        cp_async_wait<PH_DEPTH - 1>();
+        const unsigned a = slot + cs * PH_STAGE_BYTES;
+        const float4 fa = lds128(a + swz), fb = lds128(a + (swz ^ 16u));
+        const float f[8] = { fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w };
+        cs = (cs + 1u) & (PH_DEPTH - 1u);
+        const bool go = fn(blk, cur.off, f);
+        cur.next();
+        if (!go) break;
     }
-#undef PH_FETCH
-#undef PH_USE
+    cp_async_wait<0>();                             // nothing of this lane is in flight when the ring is reused or the CTA retires
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -289,8 +306,9 @@ __device__ __forceinline__ int first_wrap8(float p, const float (&f)[8], float* 
 // round A: one lane per chunk, one pass over [n0, first wrap of both trajectories inside the next chunk], the 32
 // lanes of a warp in step over the same blocks of their 32 items
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_phase_a(PlanDev P)
+__global__ void __launch_bounds__(128, PH_OCC) k_phase_a(PlanDev P)
 {
+    __shared__ __align__(16) unsigned char ring[PH_RING_BYTES];
     const PChunkLane X = pchunk_of_lane(P);
     if (!X.valid) return;
     const bool last = X.c + 1 >= X.C;             // the last chunk hands no phase on, but the scan needs its anchor
@@ -303,7 +321,7 @@ __global__ void __launch_bounds__(128) k_phase_a(PlanDev P)
     bool two = X.c == 0;                          // chunk 0 starts exact: one trajectory, no anchor needed
     // n1 is a multiple of 8 when the chunk has a successor (chunk ends are multiples of 256 but the utterance's)
     const uint32_t t_end = last ? ((n1 + 7u) & ~7u) : ((X.nn1 + 7u) & ~7u);
-    walk_blocks(P.F, U, P.chunk_len, X.n0, t_end, [&](uint32_t blk, size_t, const float (&f)[8]) -> bool {
+    walk_blocks(ring, P.F, U, P.chunk_len, X.n0, t_end, [&](uint32_t blk, size_t, const float (&f)[8]) -> bool {
         if (blk < n1) {
             if (two) {
                 steps8(p0, f);
@@ -510,8 +528,9 @@ __device__ __noinline__ uint32_t phase_b_redo_block(const float* __restrict__ F,
     return tie;
 }
 
-__global__ void __launch_bounds__(128) k_phase_b(PlanDev P, uint32_t round)
+__global__ void __launch_bounds__(128, PH_OCC) k_phase_b(PlanDev P, uint32_t round)
 {
+    __shared__ __align__(16) unsigned char ring[PH_RING_BYTES];
     if (round != 0 && P.pstats[PSTAT_PENDING + round] == 0u) return;   // nothing is dirty: the whole grid leaves
     const PChunkLane X = pchunk_of_lane(P);
     if (!X.valid) return;
@@ -536,7 +555,7 @@ __global__ void __launch_bounds__(128) k_phase_b(PlanDev P, uint32_t round)
         eb_n = 0;
     };
     const uint32_t n1f = n1 & ~7u;                  // whole blocks; only an utterance's last chunk has a ragged tail
-    walk_blocks(F, U, CL, n0, n1f, [&](uint32_t blk, size_t off, const float (&f)[8]) -> bool {
+    walk_blocks(ring, F, U, CL, n0, n1f, [&](uint32_t blk, size_t off, const float (&f)[8]) -> bool {
         float pv[8], s[8];
         bool edge = false;
 #pragma unroll

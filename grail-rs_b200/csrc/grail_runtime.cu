@@ -51,6 +51,7 @@ struct grail_ctx {
     int      formants_per_lane = 2;  // 1 or 2 formants of an utterance share one lane's clocks, noise and saw
     int      phase_mode = 1;         // 1: chunk-parallel exact carrier phase (grail_phase.cuh); 0: serial chains (+ phase scan for long utterances)
     uint32_t phase_chunk = 0;        // samples per phase chunk (multiple of 256; 0: chosen by the planner)
+    uint32_t walk_warps_per_sm = 0;  // resident warps per SM of the phase walks (occupancy query, first plan)
     int      phase_rounds = -1;      // repair rounds enqueued after the first proof (-1: by the longest utterance)
     cudaStream_t   s_copy = nullptr;    // one-shot batches: device-to-host copies of finished utterance groups
     int      e2e_groups = -1;        // one-shot batches: utterance groups whose copies overlap the next group's kernels (-1 auto)
@@ -631,8 +632,24 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
     if (ctx->phase_mode && pl->n_items) {
         uint64_t pc = ctx->phase_chunk;
         if (pc == 0) {
-            const uint64_t lanes = (uint64_t)ctx->prop.multiProcessorCount * 16ull * 32ull;
-            pc = std::min<uint64_t>(4096, std::max<uint64_t>(1024, (total / lanes) & ~255ull));
+            // a warp of the walks is one sub-range of one group of 32 items: K sub-ranges per item make n_groups * K warps.
+            // Largest K whose warps are all resident at once (one wave: a second, partial wave doubles the kernel's
+            // time) with chunks of at least 1024 samples; batches too large for that get 4096-sample chunks.
+            if (ctx->walk_warps_per_sm == 0) {
+                int nb = 0;
+                cudaFuncSetAttribute(k_phase_a, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                cudaFuncSetAttribute(k_phase_b, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_phase_b, 128, 0) != cudaSuccess || nb < 1) nb = 1;
+                cudaGetLastError();
+                ctx->walk_warps_per_sm = (uint32_t)nb * 4u;
+            }
+            const uint64_t slots = (uint64_t)ctx->prop.multiProcessorCount * ctx->walk_warps_per_sm;
+            const uint64_t cl = pl->chunk_len;
+            uint64_t K = std::max<uint64_t>(1, slots / std::max<uint32_t>(pl->n_groups, 1));
+            auto pc_of = [&](uint64_t k) { return ((cl + k - 1) / k + 255) & ~255ull; };
+            while (K > 1 && pc_of(K) < 1024) --K;
+            pc = pc_of(K);
+            if (pc > 4096) pc = 4096;
         }
         pc = std::max<uint64_t>(256, (pc + 255) & ~255ull);
         pc = std::min<uint64_t>(pc, pl->chunk_len);

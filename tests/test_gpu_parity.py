@@ -174,7 +174,7 @@ def test_relaunch_is_deterministic(ctx):
     b = plan.read_output()
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     t = plan.timings()
-    assert t["n_launches"] in (3, 4) and t["total_ms"] > 0
+    assert t["n_launches"] >= 3 and t["total_ms"] > 0
     plan.close()
 
 
