@@ -72,6 +72,7 @@ struct ItemDev {
     uint32_t pad;
 };
 
+struct DirtyRec;
 struct PlanDev {
     const float*        elems;     // n_elems_total x 52 words
     const SegRec*       segs;      // one per phoneme
@@ -88,6 +89,9 @@ struct PlanDev {
     const uint32_t*     pscan_status; // 16 words per parallel phase scan: {mismatches, done, rounds, unsupported, history[12]}
     float*              pchunks;   // chunk-parallel exact phase: per-chunk records, one array per field (grail_phase.cuh; null: serial chains only)
     uint32_t            pc_stride; // elements per field array
+    uint32_t*           pdirty;    // 2 x pc_stride chunk ids: the dirty chunks of the repair round in flight (by round parity)
+    struct DirtyRec*    pdrec;     // pc_stride records: geometry of those chunks (k_phase_chain -> k_phase_saw)
+    float*              ppark;     // [blocks per chunk][pc_stride]: phase at the start of every 8-sample block of a dirty chunk
     double*             bsum;      // sum of F_t over every 256-sample run (k_frequency), the guesses' raw material
     uint32_t*           utt_status;// per utterance: bit 0 = carrier phase proven exact by the chunk-parallel path
     uint32_t*           pstats;    // 64 words: see PSTAT_*
@@ -339,11 +343,32 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
         const bool quiet = (k0 + 8 <= count) && (time > 9.0f * dt) && (jph + 9.0f * jinc < 1.0f);
         if (quiet) { // no hand-over and no wrap inside these 8 samples: literal clocks, no event tests
             float buf[8];
+            float bsum8 = 0.0f;   // the block's sum in f32 first (8 terms of ~2^-9: the error is far below 2^-23), one f64 add per block
+            // the segment is fixed for the block and `time` only falls: the guards of div_by_const and the silent case
+            // are decided once per block, the 8 samples are then straight-line code
+            if (!seg.silent && seg.rcp_bl != 0.0f && time < 1e25f) {          // (time - 8 dt > dt > 1e-25 here)
+                const float y = seg.rcp_bl, nb = -seg.blend_len;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                buf[k] = freq_sample();
-                time = ssub(time, dt);                                                     // :861
-                jph = sadd(jph, jinc);                                                     // :242
+                for (int k = 0; k < 8; ++k) {
+                    const float q = __fmul_rn(time, y);
+                    const float alpha = fminf(__fmaf_rn(__fmaf_rn(nb, q, time), y, q), 1.0f);          // :899 (exact quotient)
+                    const float fb = sadd(smul(seg.xf, ssub(1.0f, alpha)), smul(seg.yf, alpha));    // :406
+                    const float n0 = sadd(smul(cur, ssub(1.0f, jph)), smul(nxt, jph));              // :254
+                    const float fr = sadd(fb, smul(n0, dfreq));                                     // :763
+                    odd |= !(fr >= 0.0f);
+                    bsum8 = sadd(bsum8, fr);
+                    buf[k] = fr;
+                    time = ssub(time, dt);                                                          // :861
+                    jph = sadd(jph, jinc);                                                          // :242
+                }
+                fsum += (double)bsum8;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    buf[k] = freq_sample();
+                    time = ssub(time, dt);                                                     // :861
+                    jph = sadd(jph, jinc);                                                     // :242
+                }
             }
             float4* d4 = reinterpret_cast<float4*>(dst + (k0 >> 3) * bstep);
             d4[0] = make_float4(buf[0], buf[1], buf[2], buf[3]);

@@ -53,7 +53,8 @@ enum { PCF_START = 0,   // claimed exact phase before the chunk's first sample (
        PCF_A21 = 8,
        PCF_R20 = 9,     //            phase after it
        PCF_R21 = 10,
-       PCF_COUNT = 11 };
+       PCF_TIEKEY = 11, // first round-half-even tie on a wrap step inside the chunk: (sample << 2) | 1 lower / 2 upper candidate taken; -1: none
+       PCF_COUNT = 12 };
 enum : uint32_t { PCH_DIRTY = 1u, PCH_TIE_LOWER = 2u, PCH_TIE_UPPER = 4u };
 // pstats words
 enum { PSTAT_WALKS = 0,       // chunks walked by k_phase_b, all rounds
@@ -143,6 +144,29 @@ __device__ __forceinline__ PChunkLane pchunk_of_lane(const PlanDev& P)
         len2 = min(min(PC, CL - j1), n - X.n1);
     }
     X.nn1 = X.n1 + len2;
+    return X;
+}
+
+// the same record for global chunk id g (repair rounds: the dirty chunks come as a dense list, in no particular order)
+__device__ __forceinline__ PChunkLane pchunk_of_id(const PlanDev& P, uint32_t g)
+{
+    PChunkLane X;
+    uint32_t lo = 0, hi = P.n_utts;    // last utterance with pc_first <= g (utterances without chunks share their successor's pc_first)
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (P.utts[mid].pc_first <= g) lo = mid; else hi = mid;
+    }
+    const UttDev& U = P.utts[lo];
+    const uint32_t K = P.pc_per_item, PC = P.phase_chunk, CL = P.chunk_len, n = U.n_samples;
+    X.valid = true;
+    X.u = lo;
+    X.g = g;
+    X.C = U.pc_count;
+    X.c = g - U.pc_first;
+    const uint32_t ci = X.c / K, q = X.c - ci * K;
+    X.n0 = ci * CL + q * PC;
+    X.n1 = min(ci * CL + min(q * PC + PC, CL), n);
+    X.nn1 = X.n1;
     return X;
 }
 
@@ -531,9 +555,21 @@ __device__ __noinline__ uint32_t phase_b_redo_block(const float* __restrict__ F,
 __global__ void __launch_bounds__(128, PH_OCC) k_phase_b(PlanDev P, uint32_t round)
 {
     __shared__ __align__(16) unsigned char ring[PH_RING_BYTES];
-    if (round != 0 && P.pstats[PSTAT_PENDING + round] == 0u) return;   // nothing is dirty: the whole grid leaves
-    const PChunkLane X = pchunk_of_lane(P);
-    if (!X.valid) return;
+    // Round 0 walks every chunk, a warp = one sub-range of one group of 32 items (coalesced).  The repair rounds walk the
+    // chunks k_phase_fix listed as dirty, densely packed: a few per cent of all chunks, spread over almost every warp
+    // of the round-0 mapping (lanes of a warp are 32 different utterances), so walking them in place would cost a
+    // full round's instruction issue each time (measured 158 / 123 / 76 us per round at config 2 against 363 us for
+    // round 0 itself).
+    PChunkLane X;
+    if (round == 0) {
+        X = pchunk_of_lane(P);
+        if (!X.valid) return;
+    } else {
+        const uint32_t n_dirty = P.pstats[PSTAT_PENDING + round];
+        const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n_dirty) return;                                      // (nothing dirty: the whole grid leaves)
+        X = pchunk_of_id(P, P.pdirty[(size_t)(round & 1u) * P.pc_stride + i]);
+    }
     const uint32_t g = X.g;
     if (!((uint32_t)pci(P, PCF_FLAGS)[g] & PCH_DIRTY)) return;
     const UttDev& U = P.utts[X.u];
@@ -603,10 +639,104 @@ __global__ void __launch_bounds__(128, PH_OCC) k_phase_b(PlanDev P, uint32_t rou
         }
     }
     pcf(P, PCF_END)[g] = p;
-    pci(P, PCF_FLAGS)[g] = (int32_t)tie;
+    pci(P, PCF_FLAGS)[g] = 0;
+    pci(P, PCF_TIEKEY)[g] = tie == 0u ? -1 : (tie == PCH_TIE_LOWER ? 1 : 2);   // (only the kind matters to k_phase_fix)
     if (X.c + 1 == X.C) P.utt_final[(size_t)X.u * 32 + 24] = p;   // Synthesize.phase after the last sample (stream state)
     const unsigned act = __activemask();
     if ((threadIdx.x & 31) == (unsigned)(__ffs(act) - 1)) atomicAdd(P.pstats + PSTAT_WALKS, (uint32_t)__popc(act));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Repair rounds, in two kernels.  A repair round lasts as long as one chunk walk, and k_phase_b's walk is slow when it
+// runs alone (few dirty chunks: one warp per scheduler, ~150 instructions per 8-sample block with the saw, the edge
+// tests and the stores in the loop: 1 400 - 1 600 cycles per block measured, 190 us for a 2 048-sample chunk).  So a
+// dirty chunk is re-walked as
+//   k_phase_chain   the bare chain, one lane per dirty chunk: three operations per sample, the phase at the start of
+//                   every 8-sample block parked in a scratch array -- the only serial part;
+//   k_phase_saw     one lane per dirty BLOCK: replays its 8 steps from the parked phase, forms the saw with its
+//                   polyBLEP edges, notes ties -- every block of every dirty chunk at once.
+// Same operations per sample as k_phase_b, bit-identical results.  (A warp per dirty chunk, k_phase_pair style, was
+// measured too: 196 / 102 / 26 us per round at config 2 -- fine for the last rounds, but the first one re-walks a
+// tenth of all chunks and 31 of a warp's 32 lanes repeat the same chain.)
+// ------------------------------------------------------------------------------------------------
+struct DirtyRec {           // one per dirty chunk of the round in flight (written by k_phase_chain, read by k_phase_saw)
+    unsigned long long off0;   // tiled offset of the chunk's first block
+    unsigned long long dbg0;   // index of the chunk's first sample in the linear phase tap (f_off + n0)
+    uint32_t g, n;             // chunk id, samples in the chunk
+};
+
+__global__ void __launch_bounds__(128, PH_OCC) k_phase_chain(PlanDev P, uint32_t round)
+{
+    __shared__ __align__(16) unsigned char ring[PH_RING_BYTES];
+    const uint32_t n_dirty = P.pstats[PSTAT_PENDING + round];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_dirty) return;                                          // (nothing dirty: the whole grid leaves)
+    const PChunkLane X = pchunk_of_id(P, P.pdirty[(size_t)(round & 1u) * P.pc_stride + i]);
+    const uint32_t g = X.g;
+    DirtyRec rec;
+    rec.g = g; rec.n = 0u; rec.off0 = 0ull; rec.dbg0 = 0ull;
+    if (!((uint32_t)pci(P, PCF_FLAGS)[g] & PCH_DIRTY)) { P.pdrec[i] = rec; return; }
+    const UttDev& U = P.utts[X.u];
+    const uint32_t n0 = X.n0, n1 = X.n1;
+    float p = pcf(P, PCF_START)[g];
+    float* park = P.ppark + i;                                         // block b of dirty chunk i at ppark[b * pc_stride + i]
+    const size_t stride = P.pc_stride;
+    bool first = true;
+    // whole blocks, the utterance's ragged last one included: k_frequency pads it with zeros, and p + 0 is p
+    walk_blocks(ring, P.F, U, P.chunk_len, n0, (n1 + 7u) & ~7u, [&](uint32_t blk, size_t off, const float (&f)[8]) -> bool {
+        if (first) { rec.off0 = off; first = false; }
+        park[(size_t)((blk - n0) >> 3) * stride] = p;
+        steps8(p, f);
+        return true;
+    });
+    rec.n = n1 - n0;
+    rec.dbg0 = U.f_off + n0;
+    P.pdrec[i] = rec;
+    pcf(P, PCF_END)[g] = p;
+    pci(P, PCF_FLAGS)[g] = 0;
+    pci(P, PCF_TIEKEY)[g] = -1;
+    if (X.c + 1 == X.C) P.utt_final[(size_t)X.u * 32 + 24] = p;       // Synthesize.phase after the last sample (stream state)
+    const unsigned act = __activemask();
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(act) - 1)) atomicAdd(P.pstats + PSTAT_WALKS, (uint32_t)__popc(act));
+}
+
+__global__ void __launch_bounds__(256) k_phase_saw(PlanDev P, uint32_t round)
+{
+    const uint32_t n_dirty = P.pstats[PSTAT_PENDING + round];
+    if (n_dirty == 0u) return;
+    const uint32_t nbpc = (P.phase_chunk + 7u) >> 3;                   // blocks of a full chunk
+    const unsigned long long total = (unsigned long long)n_dirty * nbpc;
+    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+    const size_t stride = P.pc_stride;
+    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += step) {
+        const uint32_t b = (uint32_t)(idx / n_dirty), i = (uint32_t)(idx - (unsigned long long)b * n_dirty);   // consecutive lanes: consecutive chunks
+        const DirtyRec rec = P.pdrec[i];
+        if (8u * b >= rec.n) continue;
+        const uint32_t valid = min(8u, rec.n - 8u * b);
+        float q = P.ppark[(size_t)b * stride + i];
+        float f[8], sv[8];
+        const size_t off = (size_t)rec.off0 + (size_t)b * 256u;
+        ldg256(P.F + off, f);
+        uint32_t key = 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            sv[k] = 0.0f;
+            if ((uint32_t)k < valid) {
+                const float pv = q;
+                float gk;
+                q = phase_step(q, f[k], gk);
+                sv[k] = fmaf(2.0f, pv, -1.0f);                                       // :517 with polyblep = 0 (2p is exact)
+                if (!((pv >= f[k]) && (pv <= ssub(1.0f, f[k])))) sv[k] = saw_edge_inl(pv, f[k]);
+                if (gk != 0.0f && key == 0xFFFFFFFFu) {
+                    const uint32_t t = wrap_tie1(pv, f[k]);
+                    if (t) key = ((8u * b + (uint32_t)k) << 2) | (t == PCH_TIE_LOWER ? 1u : 2u);
+                }
+                if (P.phase_dbg) P.phase_dbg[(size_t)rec.dbg0 + 8u * b + k] = pv;
+            }
+        }
+        stg256(P.saw + off, sv);
+        if (key != 0xFFFFFFFFu) atomicMin(reinterpret_cast<unsigned int*>(pci(P, PCF_TIEKEY)) + rec.g, key);   // the chunk's FIRST tie
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -633,13 +763,18 @@ __global__ void __launch_bounds__(128) k_phase_fix(PlanDev P, uint32_t round /* 
     const float* endp = pcf(P, PCF_END) + U.pc_first;
     int32_t* flags = pci(P, PCF_FLAGS) + U.pc_first;
     bool any = false;
-    uint32_t n_dirty = 0, n_bad = 0;
+    uint32_t n_dirty = 0, n_bad = 0;   // (n_dirty: kept for debugging)
     int din = 0;                                  // d of this block's first chunk (chunk 0: its start is exact)
+    const int32_t* tiekey = pci(P, PCF_TIEKEY) + U.pc_first;
     struct In { float e, s; uint32_t fl; };
     auto load = [&](uint32_t c) -> In {
         In x;
         x.e = x.s = 0.0f; x.fl = 0u;
-        if (c + 1 < C) { x.e = endp[c]; x.s = start[c + 1]; x.fl = (uint32_t)flags[c]; }
+        if (c + 1 < C) {
+            x.e = endp[c]; x.s = start[c + 1];
+            const int32_t k = tiekey[c];
+            x.fl = k < 0 ? 0u : ((k & 3) == 1 ? PCH_TIE_LOWER : PCH_TIE_UPPER);
+        }
         return x;
     };
     In nx = load(lane);
@@ -689,7 +824,15 @@ __global__ void __launch_bounds__(128) k_phase_fix(PlanDev P, uint32_t round /* 
                 flags[c + 1] = (int32_t)PCH_DIRTY;
             }
         }
-        n_dirty += __popc(__ballot_sync(0xffffffffu, dirty));
+        // the dirty chunks of this block go to the list the next k_phase_b walks (one atomic per block that has any)
+        const unsigned dmask = __ballot_sync(0xffffffffu, dirty);
+        if (dmask != 0u && round <= (uint32_t)PH_MAX_ROUNDS) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(P.pstats + PSTAT_PENDING + round, (uint32_t)__popc(dmask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (dirty) P.pdirty[(size_t)(round & 1u) * P.pc_stride + base + __popc(dmask & ((1u << lane) - 1u))] = U.pc_first + c + 1;
+        }
+        n_dirty += __popc(dmask);
     }
     if (lane == 0) {
         if (!any) {
@@ -697,7 +840,6 @@ __global__ void __launch_bounds__(128) k_phase_fix(PlanDev P, uint32_t round /* 
         } else {
             atomicAdd(P.pstats + PSTAT_MISMATCH, n_bad);
             if (round <= (uint32_t)PH_MAX_ROUNDS) {
-                atomicAdd(P.pstats + PSTAT_PENDING + round, n_dirty);
                 atomicMax(P.pstats + PSTAT_ROUNDS, round);
             } else {
                 atomicAdd(P.pstats + PSTAT_UNPROVEN, 1u);

@@ -157,7 +157,7 @@ struct grail_plan {
     std::vector<PScanDev> pscans;          // exact parallel phase scans (one per long utterance)
     std::vector<uint32_t> pscan_utt;
     uint32_t* d_pscan_status = nullptr;
-    float* d_pchunks = nullptr; uint32_t pc_stride = 0; double* d_bsum = nullptr; uint32_t* d_utt_status = nullptr; uint32_t* d_pstats = nullptr;
+    float* d_pchunks = nullptr; DirtyRec* d_pdrec = nullptr; float* d_ppark = nullptr; uint32_t pc_stride = 0; double* d_bsum = nullptr; uint32_t* d_utt_status = nullptr; uint32_t* d_pstats = nullptr;
     uint32_t n_pchunks = 0, phase_chunk = 0, max_pchunks = 0, pc_per_item = 1;   // phase_chunk == 0: serial chains only
     bool select_on_device = false;   // d_elems was written by k_select from phoneme-level input
     std::vector<void*> pscan_bufs;
@@ -377,6 +377,9 @@ static PlanDev plan_dev(const grail_plan* pl, bool with_dbg, int slot = 0)
     P.utt_init = pl->d_utt_init;
     P.utt_final = pl->d_utt_final;
     P.pchunks = pl->phase_chunk ? pl->d_pchunks : nullptr;
+    P.pdrec = pl->d_pdrec;
+    P.ppark = pl->d_ppark;
+    P.pdirty = pl->phase_chunk ? reinterpret_cast<uint32_t*>(pl->d_pchunks + (size_t)pl->pc_stride * PCF_COUNT) : nullptr;
     P.bsum = pl->phase_chunk ? pl->d_bsum : nullptr;
     P.utt_status = pl->d_utt_status;
     P.pstats = pl->d_pstats;
@@ -399,7 +402,7 @@ static void plan_release(grail_plan* pl)
     ctx->live_plans.erase(std::remove(ctx->live_plans.begin(), ctx->live_plans.end(), pl), ctx->live_plans.end());
     void* bufs[] = { pl->d_elems, pl->d_segs, pl->d_utts, pl->d_items, pl->d_jscheds, pl->d_jrecs, pl->d_F, pl->d_saw,
                      pl->d_phase_dbg, pl->d_err, pl->d_out, pl->d_fflags, pl->d_utt_init, pl->d_utt_final,
-                     pl->d_pchunks, pl->d_bsum, pl->d_utt_status, pl->d_pstats };
+                     pl->d_pchunks, pl->d_bsum, pl->d_utt_status, pl->d_pstats, pl->d_pdrec, pl->d_ppark };
     for (void* b : bufs) pool_free(ctx, b);
     for (void* b : pl->pscan_bufs) pool_free(ctx, b);
     pool_free(ctx, pl->slot[1].F); pool_free(ctx, pl->slot[1].fflags); pool_free(ctx, pl->slot[1].saw);
@@ -629,7 +632,11 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
     //      warps of walks per SM (the walks are streaming kernels), at least 1024 samples (a chunk without a carrier
     //      wrap has no anchor: shorter chunks fail their proofs more often), at most 4096.
     pl->phase_chunk = 0;
-    if (ctx->phase_mode && pl->n_items) {
+    // (A handful of very long utterances -- config 3 -- keep the fixed-point phase scan of grail_kernels.cuh: the
+    //  chunk-parallel path scans an utterance's chunk records with ONE warp per utterance in k_phase_guess / _scan_a /
+    //  _fix, which is the wrong shape for 25 000 chunks of a single utterance: measured 5.8 ms against 3.3 ms.)
+    const bool few_long = ctx->phase_mode == 1 && n_utts <= 16 && n_max >= ctx->pscan_min;
+    if (ctx->phase_mode && !few_long && pl->n_items) {
         uint64_t pc = ctx->phase_chunk;
         if (pc == 0) {
             // a warp of the walks is one sub-range of one group of 32 items: K sub-ranges per item make n_groups * K warps.
@@ -645,11 +652,24 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
             }
             const uint64_t slots = (uint64_t)ctx->prop.multiProcessorCount * ctx->walk_warps_per_sm;
             const uint64_t cl = pl->chunk_len;
-            uint64_t K = std::max<uint64_t>(1, slots / std::max<uint32_t>(pl->n_groups, 1));
             auto pc_of = [&](uint64_t k) { return ((cl + k - 1) / k + 255) & ~255ull; };
-            while (K > 1 && pc_of(K) < 1024) --K;
-            pc = pc_of(K);
-            if (pc > 4096) pc = 4096;
+            // Cost model (in units of one chunk walk of one sample): round 0 streams every chunk, wave after wave of
+            // `slots` resident warps, so it lasts about ceil(waves) * PC (a partial second wave costs a whole one);
+            // every repair round is latency-bound and lasts one chunk walk, about 4x slower per sample than the
+            // bandwidth-bound round 0 (measured), two to three rounds per launch.  Chunks shorter than 1024 samples lose
+            // their anchor (a chunk needs a carrier wrap) and fail their proofs far more often; 4096 is the upper end.
+            uint64_t best_k = 1;
+            double best = 1e300;
+            for (uint64_t k = 1; k <= std::max<uint64_t>(1, cl / 1024) + 1; ++k) {
+                const uint64_t p_ = pc_of(k);
+                if (k > 1 && p_ < 1024) break;
+                if (p_ > 4096 && pc_of(k + 1) >= 1024) continue;
+                const uint64_t warps = (uint64_t)pl->n_groups * ((cl + p_ - 1) / p_);
+                const double waves = std::ceil((double)warps / (double)slots);
+                const double cost = waves * (double)p_ + 2.5 * 4.0 * (double)p_ / 8.0;
+                if (cost < best) { best = cost; best_k = k; }
+            }
+            pc = pc_of(best_k);
         }
         pc = std::max<uint64_t>(256, (pc + 255) & ~255ull);
         pc = std::min<uint64_t>(pc, pl->chunk_len);
@@ -744,7 +764,9 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
     PA(pl->d_pstats, 256);
     if (pl->phase_chunk) {
         pl->pc_stride = (pl->n_pchunks + 64u) & ~31u;
-        PA(pl->d_pchunks, (size_t)pl->pc_stride * PCF_COUNT * sizeof(float));
+        PA(pl->d_pchunks, (size_t)pl->pc_stride * (PCF_COUNT + 2) * sizeof(float));   // + the two dirty lists
+        PA(pl->d_pdrec, (size_t)pl->pc_stride * sizeof(DirtyRec));
+        PA(pl->d_ppark, (size_t)pl->pc_stride * ((pl->phase_chunk + 7) / 8) * sizeof(float));
         PA(pl->d_bsum, (pl->f_words / 256 + 2) * sizeof(double));
     }
     for (uint32_t u : pl->pscan_utt) {
@@ -935,6 +957,12 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
         // chunk-parallel exact phase (grail_phase.cuh): guess, round A, scan, round B, then proof / repair rounds
         const unsigned wg = (unsigned)(((uint64_t)pl->n_utts * 32 + 127) / 128);
         const unsigned cg = (unsigned)(((uint64_t)pl->n_groups * pl->pc_per_item + 3) / 4);   // a warp = one sub-range of one group of 32 items
+        // repair rounds walk a dense list of dirty chunks whose length only the device knows: the grid covers the
+        // worst case (every chunk dirty) and the CTAs past the list's end leave at once
+        // repair rounds walk a dense list of dirty chunks whose length only the device knows: k_phase_chain's grid covers
+        // the worst case (every chunk dirty; CTAs past the list's end leave at once), k_phase_saw strides over the blocks
+        const unsigned dg = (pl->n_pchunks + 127) / 128;
+        const unsigned dgs = (unsigned)ctx->prop.multiProcessorCount * 8u;
         k_phase_guess<<<wg, 128, 0, s>>>(P);
         pl->last_launches++;
         if (pl->max_pchunks > 1) {
@@ -952,8 +980,9 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
         if (pl->max_pchunks <= 1) rounds = 0;
         for (int r = 1; r <= rounds; ++r) {
             k_phase_fix<<<wg, 128, 0, s>>>(P, (uint32_t)r);
-            k_phase_b<<<cg, 128, 0, s>>>(P, (uint32_t)r);
-            pl->last_launches += 2;
+            k_phase_chain<<<dg, 128, 0, s>>>(P, (uint32_t)r);
+            k_phase_saw<<<dgs, 256, 0, s>>>(P, (uint32_t)r);
+            pl->last_launches += 3;
         }
         k_phase_fix<<<wg, 128, 0, s>>>(P, (uint32_t)PH_MAX_ROUNDS + 1u);   // the final proof: sets the status bits
         pl->last_launches++;
@@ -1120,7 +1149,7 @@ int grail_cuda_set_option(grail_ctx* ctx, const char* key, double value)
     } else if (!strcmp(key, "e2e_groups")) {
         ctx->e2e_groups = value < 0.0 ? -1 : (int)value;
     } else if (!strcmp(key, "phase_mode")) {
-        ctx->phase_mode = value != 0.0;
+        ctx->phase_mode = value == 0.0 ? 0 : (value == 2.0 ? 2 : 1);   // 2: chunk-parallel even for a few long utterances
     } else if (!strcmp(key, "phase_chunk")) {
         if (value != 0.0 && !(value >= 256.0 && value <= 1048576.0)) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "phase_chunk out of range [256, 2^20] (0 = auto)");
         ctx->phase_chunk = (uint32_t)value;

@@ -217,16 +217,18 @@ int  grail_cuda_plan_timings(const grail_plan* plan, grail_timings* out);
  * for the most recent launch. */
 int  grail_cuda_plan_phase_scan_stats(grail_plan* plan, uint32_t* stats);
 /* The carrier phase (src/lib.rs:520-525) is computed exactly AND in parallel over time chunks of option "phase_chunk"
- * samples (default 2048; option "phase_mode" = 0 falls back to one serial chain per utterance): every chunk is walked
- * from a start phase derived from its neighbours, and the result is accepted only when each chunk's end equals the
- * next chunk's start bit for bit (a proof by induction from the exact phase at sample 0); mismatching chunks are
- * shifted and walked again for up to option "phase_rounds" rounds, and an utterance that is still unproven then gets the
- * serial chain.  stats[8] of the most recent launch = {phase chunks in the plan, chunks walked in all rounds together,
- * utterances that fell back to the serial chain, last repair round that was needed (0 = none), chunk boundaries that
- * failed a proof, phase_chunk, W, 0}, where W counts the (time chunk, formant) pairs of the filter kernel whose
- * decay-bounded warm-up reached all the way back to sample 0: a formant that rings longer than the utterance has lasted
- * is recomputed from the start by every later chunk (exact, but its time parallelism is gone -- a performance cliff
- * that would otherwise be silent; 0 for ordinary voices). */
+ * samples (0 = chosen by the planner, 1024-4096; option "phase_mode" = 0 falls back to one serial chain per utterance,
+ * 1 (default) = chunk-parallel except for plans of at most 16 utterances with one of >= "pscan_min_samples", which keep
+ * the phase scan above, 2 = chunk-parallel always): every chunk is walked from a start phase derived from its
+ * neighbours, and the result is accepted only when each chunk's end equals the next chunk's start bit for bit (a proof
+ * by induction from the exact phase at sample 0); mismatching chunks are shifted and walked again for up to option
+ * "phase_rounds" rounds, and an utterance that is still unproven then gets the serial chain.  stats[8] of the most
+ * recent launch = {phase chunks in the plan, chunks walked in all rounds together, utterances that fell back to the
+ * serial chain, last repair round that was needed (0 = none), chunk boundaries that failed a proof, phase_chunk, W, 0},
+ * where W counts the (time chunk, formant) pairs of the filter kernel whose decay-bounded warm-up reached all the way
+ * back to sample 0: a formant that rings longer than the utterance has lasted is recomputed from the start by every
+ * later chunk (exact, but its time parallelism is gone -- a performance cliff that would otherwise be silent; 0 for
+ * ordinary voices). */
 int  grail_cuda_plan_phase_stats(grail_plan* plan, uint32_t* stats);
 /* debug / parity taps, host buffers of total_samples entries; any may be NULL:
  * the bit-exact fundamental F_t, the carrier phase BEFORE each sample, and the polyBLEP saw */

@@ -26,9 +26,9 @@ def test_config3_long_form(ctx, oracle):
     assert plan.total_samples == 26457161
     plan.launch()
     out = plan.read_output()
-    ps = plan.phase_stats()
+    ps = plan.phase_scan_stats()
     print(plan.timings(), ps)
-    assert ps["chunks"] > 1000 and ps["unproven_utterances"] == 0, ps          # parallel-in-time phase, proven; no serial chain
+    assert ps["scans"] == 1 and ps["converged"] == 1 and ps["refused"] == 0      # parallel-in-time phase scan, no serial chain
     f, ph, saw = plan.read_intermediates()
     want, tr, fin = oracle.synthesize(elems, vp[0], trace=True)
     assert np.array_equal(f.view(np.uint32), tr["frequency"].view(np.uint32))          # bit-exact fundamental
@@ -37,6 +37,24 @@ def test_config3_long_form(ctx, oracle):
     print(st)
     assert st["max_abs"] <= MAX_ABS and st["snr_db"] >= MIN_SNR_DB, st
     plan.close()
+
+
+def test_long_form_chunk_parallel_phase(ctx, oracle):
+    """the chunk-parallel walk forced onto one long utterance (phase_mode 2; 120 phonemes, 2.6 M samples, ~1 300 chunks
+    scanned by a single warp): carrier phase bit-exact, every utterance proven"""
+    elems, offs, vp = W.from_phonemes([W.config3_phonemes(120)], g.voices.generic(), [0])
+    ctx.set_option("phase_mode", 2)
+    try:
+        plan = ctx.plan(elems, offs, vp)
+        plan.launch()
+        ps = plan.phase_stats()
+        assert ps["chunks"] > 500 and ps["unproven_utterances"] == 0, ps
+        f, ph, saw = plan.read_intermediates()
+        want, tr, _ = oracle.synthesize(elems, vp[0], trace=True)
+        assert np.array_equal(ph.view(np.uint32), tr["carrier_phase"].view(np.uint32))
+        plan.close()
+    finally:
+        ctx.set_option("phase_mode", 1)
 
 
 def test_config4_random_voices_sharded_shape(ctx, oracle):
