@@ -451,6 +451,14 @@ def run_ours(args):
         cfg4 = {"load_imbalance_max_over_mean": max(loads) / (sum(loads) / len(loads)), "samples_per_rank": loads,
                 "parity": par_all}
         if args.gather and world > 1:
+            # (the first all_gather of a process pays NCCL's channel set-up and buffer registration -- 0.7 s was seen at
+            #  N = 4 --, so one small warm-up collective goes first and the full gather is timed on its second run)
+            warm = torch.zeros(1 << 20, dtype=torch.float32, device="cuda")
+            warm_all = torch.empty(world << 20, dtype=torch.float32, device="cuda")
+            D.dist.all_gather_into_tensor(warm_all, warm)
+            del warm, warm_all
+            full = sharding.gather_outputs(out, extra["counts"][extra["assign"][rank]], extra["assign"], extra["counts"], ctx=ctx)
+            del full
             D.barrier()
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record()

@@ -1265,8 +1265,14 @@ struct FormantLane {
 #ifndef KF_ALG2
 #define KF_ALG2 0
 #endif
+#ifndef KF_RING
+#define KF_RING 0      // measured slower (see k_formant): kept as a build option for the record
+#endif
 template <int FPT> struct FormantCfg { static constexpr int warps_per_sm = 24; };   // 80 registers per lane
-template <> struct FormantCfg<2> { static constexpr int warps_per_sm = 12; };       // up to 168 registers per lane
+#ifndef KF_WARPS2
+#define KF_WARPS2 12
+#endif
+template <> struct FormantCfg<2> { static constexpr int warps_per_sm = KF_WARPS2; };       // 12: up to 168 registers per lane
 
 template <int NW, int FPT>
 __global__ void __launch_bounds__(NW * 32, FormantCfg<FPT>::warps_per_sm / NW)
@@ -1276,7 +1282,19 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
     // 128-bit row writes and the 8-lanes-per-row 128-bit reads of the reduction are bank-conflict free
     // (static shared memory ends at 48 KB: instantiations with many formant groups fall back to 32-sample tiles)
     constexpr int KT = (NW * 32 * (KF_TILE + 4) * 4 + 1024 <= 49152) ? KF_TILE : 32;
-    __shared__ __align__(16) float part[NW][32][KT + 4];
+    // KF_RING (a build option, OFF: measured 1.66 ms against 1.45 ms at config 2 and 5.06 against 4.17 ms on a config-4
+    // slice -- the reducer warp alone is slower than all warps sharing the rows between two barriers).
+    // In instantiations with 2-4 warps the CTA-wide reduction of the partial sums is taken off the common path.
+    // The LAST warp is the reducer: the others (producers) only park their partial sums in a two-deep ring of tiles
+    // and signal an mbarrier per 32-sample batch; the reducer waits for them, adds the tiles in formant order and
+    // stores.  No __syncthreads in the loop, and the warm-up imbalance between the warps (the first warp holds the
+    // formants that ring longest: 3 590 against 1 450 samples of warm-up with the default voice) pays for the
+    // reducer's extra work instead of being waited out at a barrier.
+    constexpr bool RING = (KF_RING != 0) && NW >= 2 && NW <= 4 && KT == 32;
+    constexpr int RB = RING ? 2 : 1;
+    __shared__ __align__(16) float part_all[RB][NW][32][KT + 4];
+    __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+    float (*part)[32][KT + 4] = part_all[0];
     __shared__ unsigned long long row_out[32];
     __shared__ uint32_t row_len[32];
 
@@ -1490,7 +1508,11 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
         }
     };
 
-    __syncthreads();   // row_out / row_len visible
+    if (RING && threadIdx.x == 0) {
+        mbar_init(&s_full[0], NW - 1); mbar_init(&s_full[1], NW - 1);
+        mbar_init(&s_empty[0], 1); mbar_init(&s_empty[1], 1);
+    }
+    __syncthreads();   // row_out / row_len (and the barriers) visible
     uint32_t lmax = 0;
 #pragma unroll 1
     for (int r = 0; r < 32; ++r) lmax = max(lmax, row_len[r]);
@@ -1520,7 +1542,10 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
     const int r_lo = on ? -(int)wmine : 0x7fffffff;
     const int r_hi = on ? (int)it.len : (int)0x80000000;
     if (-(int)wmax >= r_lo && -(int)wmax < r_hi) fetch();
-    const unsigned part_a = (unsigned)__cvta_generic_to_shared(&part[w][lane][0]);
+    unsigned part_a = (unsigned)__cvta_generic_to_shared(&part_all[0][w][lane][0]);   // (RING: moves to the batch's tile)
+    const unsigned part_a0 = part_a;
+    constexpr unsigned SLOT_BYTES = (unsigned)(NW * 32 * (KT + 4) * 4);
+    const unsigned full_a = (unsigned)__cvta_generic_to_shared(&s_full[0]), empty_a = (unsigned)__cvta_generic_to_shared(&s_empty[0]);
 
     Coef cend[FPT];        // coefficients at the current clock values (the next block's start point)
     bool c_valid = false;
@@ -1739,12 +1764,30 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
             sts128(part_a + (r & (KT - 1)) * 4 + 16, v[4], v[5], v[6], v[7]);
             if ((r & (KT - 1)) == KT - 8) {
                 const uint32_t base = (uint32_t)r - (uint32_t)(KT - 8);
-                __syncthreads();
+                const uint32_t kb = base / (uint32_t)KT, slot = kb & 1u, use = kb >> 1;   // (RING) batch, its tile, the tile's n-th use
+                bool reduce_here = true;
+                int rc0 = w * 4, rcs = NW * 4;
+                if (RING) {
+                    __syncwarp();
+                    if (w < NW - 1) {
+                        // producer: this batch's tile is complete; the next batch goes to the other tile, once the reducer
+                        // has emptied it (its previous use was batch kb - 1)
+                        if (lane == 0) mbar_arrive(full_a + slot * 8u);
+                        if (kb >= 1u) mbar_wait(empty_a + (slot ^ 1u) * 8u, ((kb - 1u) >> 1) & 1u);
+                        reduce_here = false;
+                    } else {
+                        mbar_wait(full_a + slot * 8u, use & 1u);
+                        rc0 = 0; rcs = 4;                      // the reducer takes all 32 rows
+                    }
+                    part = part_all[slot];
+                } else {
+                    __syncthreads();
+                }
                 // 8 lanes per row, 4 rows per pass: sum the formant groups in index order (Array::sum, :123),
                 // scale (:574), store 16 bytes per lane = 128 contiguous bytes per row
                 const int sub = lane >> 3, l8 = lane & 7;
 #pragma unroll 1
-                for (int rc = w * 4 + sub; rc < 32 * (KT / 32); rc += NW * 4) {
+                for (int rc = rc0 + sub; reduce_here && rc < 32 * (KT / 32); rc += rcs) {
                     const int row = rc & 31, cb = (rc >> 5) * 32;          // (row, 32-sample column block) of the tile
                     const uint32_t rl = row_len[row];
                     const uint32_t s0 = base + cb + l8 * 4;
@@ -1792,7 +1835,15 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
                         }
                     }
                 }
-                __syncthreads();
+                if (RING) {
+                    if (w == NW - 1) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(empty_a + slot * 8u);      // the tile may be written again
+                    }
+                    part_a = part_a0 + (slot ^ 1u) * SLOT_BYTES;              // every warp: the next batch's tile
+                } else {
+                    __syncthreads();
+                }
             }
         }
     }

@@ -230,15 +230,23 @@ __device__ __forceinline__ void walk_blocks(unsigned char* ring, const float* __
     };
 #pragma unroll
     for (int i = 0; i < PH_DEPTH - 1; ++i) issue();
-    uint32_t cs = 0;
+    // the block being stepped sits in registers, and the NEXT one is read out of the ring before the stepping starts,
+    // so the shared-memory latency hides behind the dependent chain instead of heading every iteration
+    issue();
+    cp_async_wait<PH_DEPTH - 1>();
+    float4 na = lds128(slot + swz), nb = lds128(slot + (swz ^ 16u));
+    uint32_t cs = 1;
 #pragma unroll 1
     for (uint32_t blk = t0; blk < t1; blk += 8u) {
-        issue();
-        cp_async_wait<PH_DEPTH - 1>();
-        const unsigned a = slot + cs * PH_STAGE_BYTES;
-        const float4 fa = lds128(a + swz), fb = lds128(a + (swz ^ 16u));
-        const float f[8] = { fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w };
-        cs = (cs + 1u) & (PH_DEPTH - 1u);
+        const float f[8] = { na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w };
+        if (blk + 8u < t1) {
+            issue();
+            cp_async_wait<PH_DEPTH - 1>();
+            const unsigned a = slot + cs * PH_STAGE_BYTES;
+            na = lds128(a + swz);
+            nb = lds128(a + (swz ^ 16u));
+            cs = (cs + 1u) & (PH_DEPTH - 1u);
+        }
         const bool go = fn(blk, cur.off, f);
         cur.next();
         if (!go) break;
@@ -665,51 +673,77 @@ struct DirtyRec {           // one per dirty chunk of the round in flight (writt
     uint32_t g, n;             // chunk id, samples in the chunk
 };
 
-__global__ void __launch_bounds__(128, PH_OCC) k_phase_chain(PlanDev P, uint32_t round)
+// One warp per CTA, a lane per dirty chunk.  The chain runs out of shared memory, 256 samples of every lane at a time:
+// all 64 cp.async of a stage are issued at once (one DRAM round trip for 32 blocks) and WAITED FOR before the stepping
+// starts.  (A ring that keeps copies in flight while the lane steps -- walk_blocks -- is right for round 0, where two
+// dozen warps per SM hide each other's waits, but a lone warp gets nothing from it: ncu shows every shared-memory read
+// parked behind the cp.async issued just before it, a full DRAM latency per 8-sample block, 1 000 cycles.)
+constexpr uint32_t PCH_STAGE = 256;                   // samples per lane and stage
+constexpr uint32_t PCH_ROW = PCH_STAGE + 4;           // floats per lane row: conflict-free 128-bit reads
+
+__global__ void __launch_bounds__(32) k_phase_chain(PlanDev P, uint32_t round)
 {
-    __shared__ __align__(16) unsigned char ring[PH_RING_BYTES];
+    __shared__ __align__(16) float sF[32 * PCH_ROW];
     const uint32_t n_dirty = P.pstats[PSTAT_PENDING + round];
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_dirty) return;                                          // (nothing dirty: the whole grid leaves)
-    const PChunkLane X = pchunk_of_id(P, P.pdirty[(size_t)(round & 1u) * P.pc_stride + i]);
-    const uint32_t g = X.g;
-    DirtyRec rec;
-    rec.g = g; rec.n = 0u; rec.off0 = 0ull; rec.dbg0 = 0ull;
-    if (!((uint32_t)pci(P, PCF_FLAGS)[g] & PCH_DIRTY)) { P.pdrec[i] = rec; return; }
-    const UttDev& U = P.utts[X.u];
-    const uint32_t n0 = X.n0, n1 = X.n1;
-    float p = pcf(P, PCF_START)[g];
-    float* park = P.ppark + i;                                         // block b of dirty chunk i at ppark[b * pc_stride + i]
+    const uint32_t lane = threadIdx.x;
+    const unsigned row_a = (unsigned)__cvta_generic_to_shared(sF) + lane * (PCH_ROW * 4u);
     const size_t stride = P.pc_stride;
-    bool first = true;
-    // whole blocks, the utterance's ragged last one included: k_frequency pads it with zeros, and p + 0 is p
-    walk_blocks(ring, P.F, U, P.chunk_len, n0, (n1 + 7u) & ~7u, [&](uint32_t blk, size_t off, const float (&f)[8]) -> bool {
-        if (first) { rec.off0 = off; first = false; }
-        park[(size_t)((blk - n0) >> 3) * stride] = p;
-        steps8(p, f);
-        return true;
-    });
-    rec.n = n1 - n0;
-    rec.dbg0 = U.f_off + n0;
-    P.pdrec[i] = rec;
-    pcf(P, PCF_END)[g] = p;
-    pci(P, PCF_FLAGS)[g] = 0;
-    pci(P, PCF_TIEKEY)[g] = -1;
-    if (X.c + 1 == X.C) P.utt_final[(size_t)X.u * 32 + 24] = p;       // Synthesize.phase after the last sample (stream state)
-    const unsigned act = __activemask();
-    if ((threadIdx.x & 31) == (unsigned)(__ffs(act) - 1)) atomicAdd(P.pstats + PSTAT_WALKS, (uint32_t)__popc(act));
+    for (uint32_t base = blockIdx.x * 32u; base < n_dirty; base += gridDim.x * 32u) {
+        const uint32_t i = base + lane;
+        if (i >= n_dirty) continue;
+        const PChunkLane X = pchunk_of_id(P, P.pdirty[(size_t)(round & 1u) * P.pc_stride + i]);
+        const uint32_t g = X.g;
+        DirtyRec rec;
+        rec.g = g; rec.n = 0u; rec.off0 = 0ull; rec.dbg0 = 0ull;
+        if (!((uint32_t)pci(P, PCF_FLAGS)[g] & PCH_DIRTY)) { P.pdrec[i] = rec; continue; }
+        const UttDev& U = P.utts[X.u];
+        const uint32_t n0 = X.n0, n1 = X.n1;
+        TileCursor tc;                                                  // the chunk lies inside one work item:
+        tc.seek(U, n0, P.chunk_len);                                    // its blocks are 256 floats apart in the tiled arrays
+        const float* src = P.F + tc.off;
+        float* park = P.ppark + i;                                      // block b of dirty chunk i at ppark[b * pc_stride + i]
+        // whole blocks, the utterance's ragged last one included: k_frequency pads it with zeros, and p + 0 is p
+        const uint32_t nblk = (n1 - n0 + 7u) >> 3;
+        float p = pcf(P, PCF_START)[g];
+        for (uint32_t b0 = 0; b0 < nblk; b0 += PCH_STAGE / 8u) {
+            const uint32_t nb = min(PCH_STAGE / 8u, nblk - b0);
+#pragma unroll 4
+            for (uint32_t b = 0; b < nb; ++b) {
+                cp_async16(row_a + b * 32u, src + (size_t)(b0 + b) * 256u);
+                cp_async16(row_a + b * 32u + 16u, src + (size_t)(b0 + b) * 256u + 4u);
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            float4 fa = lds128(row_a), fb = lds128(row_a + 16u);
+#pragma unroll 1
+            for (uint32_t b = 0; b < nb; ++b) {
+                const float f[8] = { fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w };
+                if (b + 1 < nb) { fa = lds128(row_a + (b + 1) * 32u); fb = lds128(row_a + (b + 1) * 32u + 16u); }
+                park[(size_t)(b0 + b) * stride] = p;
+                steps8(p, f);
+            }
+        }
+        rec.off0 = tc.off;
+        rec.n = n1 - n0;
+        rec.dbg0 = U.f_off + n0;
+        P.pdrec[i] = rec;
+        pcf(P, PCF_END)[g] = p;
+        pci(P, PCF_FLAGS)[g] = 0;
+        pci(P, PCF_TIEKEY)[g] = -1;
+        if (X.c + 1 == X.C) P.utt_final[(size_t)X.u * 32 + 24] = p;    // Synthesize.phase after the last sample (stream state)
+        atomicAdd(P.pstats + PSTAT_WALKS, 1u);
+    }
 }
 
 __global__ void __launch_bounds__(256) k_phase_saw(PlanDev P, uint32_t round)
 {
     const uint32_t n_dirty = P.pstats[PSTAT_PENDING + round];
     if (n_dirty == 0u) return;
-    const uint32_t nbpc = (P.phase_chunk + 7u) >> 3;                   // blocks of a full chunk
-    const unsigned long long total = (unsigned long long)n_dirty * nbpc;
-    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+    // grid: y = block index inside the chunk, x strides over the dirty chunks (consecutive lanes: consecutive chunks, so the
+    // parked phases and the records are read coalesced; no index arithmetic beyond an add)
+    const uint32_t b = blockIdx.y;
     const size_t stride = P.pc_stride;
-    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += step) {
-        const uint32_t b = (uint32_t)(idx / n_dirty), i = (uint32_t)(idx - (unsigned long long)b * n_dirty);   // consecutive lanes: consecutive chunks
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_dirty; i += gridDim.x * blockDim.x) {
         const DirtyRec rec = P.pdrec[i];
         if (8u * b >= rec.n) continue;
         const uint32_t valid = min(8u, rec.n - 8u * b);

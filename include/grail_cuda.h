@@ -111,7 +111,7 @@ const char* grail_cuda_last_error(const grail_ctx* ctx);
 /* the ctx's cudaStream_t as an opaque pointer (for event timing / interop) */
 void* grail_cuda_stream_handle(grail_ctx* ctx);
 int  grail_cuda_synchronize(grail_ctx* ctx);
-/* tuning knobs: "warmup_nepers" (float, filter warm-up depth, default 13.8 ~ 1e-6),
+/* tuning knobs: "warmup_nepers" (float, filter warm-up depth, default 11.5 ~ 1e-5),
  * "target_lanes" (int, time-chunks the planner aims for), "max_chunk" / "min_chunk" (samples),
  * "formants_per_lane" (1|2), "pipeline" (0|1: overlap consecutive launches of a plan), "e2e_groups", "phase_mode",
  * "phase_chunk", "phase_rounds" (see grail_cuda_plan_phase_stats), "pscan_min_samples",

@@ -12,7 +12,7 @@ want = [O.synthesize(elems[offs[u]:offs[u+1]], vp[u])[0] for u in range(4)]
 want4 = [O.synthesize(e4[o4[u]:o4[u+1]], v4[u])[0] for u in range(6)]
 for chunk in (1 << 22, 6912, 2048):
     ctx.set_option("min_chunk", chunk); ctx.set_option("target_lanes", 1 if chunk > 100000 else 1 << 20)
-    for D in (6.9, 9.2, 11.5, 13.8, 16.1, 20.0):
+    for D in (9.2, 10.4, 11.5, 13.8):
         ctx.set_option("warmup_nepers", D)
         out, oo = ctx.synthesize_batch(elems, offs, vp)
         st = [W.parity_stats(out[oo[u]:oo[u+1]], want[u]) for u in range(4)]

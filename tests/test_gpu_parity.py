@@ -209,14 +209,14 @@ def test_full_size_config2_properties(ctx, oracle):
     assert np.isfinite(out).all()
     # (bit-reproducible for a fixed batch; across lanes the exact/interpolated block choice is made per warp, so twins
     #  agree to rounding level, like two different chunkings of the same utterance)
-    assert np.abs(out[oo[0]:oo[1]] - out[oo[twin]:oo[twin + 1]]).max() < 1e-6
+    assert np.abs(out[oo[0]:oo[1]] - out[oo[twin]:oo[twin + 1]]).max() < 5e-6
     # ... and a different seed on the same phonemes gives different audio
     vp2 = vp[[0, twin]].copy()
     vp2["jitter_seed"][1] = 12345
     e2 = np.concatenate([elems[offs[0]:offs[1]], elems[offs[twin]:offs[twin + 1]]])
     o2, oo2 = ctx.synthesize_batch(e2, np.array([0, 10, 20], np.uint32), vp2)
     # (a different batch is chunked differently, so equality is at warm-up precision, not bit level)
-    assert np.abs(o2[:oo2[1]] - out[oo[0]:oo[1]]).max() < 1e-6
+    assert np.abs(o2[:oo2[1]] - out[oo[0]:oo[1]]).max() < 5e-6
     assert np.abs(o2[oo2[1]:] - o2[:oo2[1]]).max() > 1e-3
     # all 1 024 utterances against the oracle (multi-threaded, about a second per host core-dozen)
     import os
