@@ -275,10 +275,14 @@ __device__ __forceinline__ FreqSeg load_freq_seg(const float* ue, uint32_t p, ui
 // closed form at the run start, then replayed literally; the scalar frequency path uses strict ops in
 // the reference's order (blend :406, value-noise lerp :254, jitter add :763).
 // ------------------------------------------------------------------------------------------------
-constexpr int FREQ_RUN = 256;   // samples per lane: amortises the two closed-form clock fast-forwards; short enough that
-                                // the last partial wave stays small (measured 512 / 256 / 128: 0.41 / 0.36 / 0.40 ms)
+// Samples per lane: `run_len`, a multiple of 256 chosen per plan.  The lane's start-up -- two binary searches, two
+// closed-form clock fast-forwards, an LCG jump -- is paid once per run; with the straight-line quiet blocks it was more
+// than half of the kernel's samples at 256 (ncu).  Measured: 0.344 / 0.295 / 0.312 ms at 256 / 512 / 1024 for config 2
+// (one voice, interleaved chunks), but 0.478 / 0.648 / 0.605 ms on a config-4 slice (a voice per utterance, whole
+// utterances as items): the planner takes 512 when the batch shares one jitter schedule and 256 otherwise.
+constexpr int FREQ_RUN_MAX = 512;
 
-__global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_item)
+__global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_item, uint32_t run_len)
 {
     // lanes of a warp = consecutive runs of one item (measured against "the same run of 32 consecutive items", which
     // lines events up across lanes but scatters every per-utterance load: 0.36 vs 0.39 ms at config 2)
@@ -287,9 +291,9 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
     const uint32_t run = (uint32_t)(t % runs_per_item);
     if (item >= P.n_items) return;
     const ItemDev it = P.items[item];
-    const uint32_t off = run * FREQ_RUN;
+    const uint32_t off = run * run_len;
     if (off >= it.len) return;
-    const uint32_t count = min((uint32_t)FREQ_RUN, it.len - off);
+    const uint32_t count = min(run_len, it.len - off);
     const uint32_t ns = it.n0 + off;
     const UttDev& U = P.utts[it.utt];
     const float* ue = P.elems + (size_t)U.elem_first * SEQ_WORDS;
@@ -339,6 +343,10 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
         if (k0 != 0 && (k0 & 127u) == 0) {   // one flag word per 128 samples (f_off, n0 and the run start are 128-aligned)
             P.fflags[(U.f_off + ns + k0 - 128) >> 7] = odd ? 1u : 0u;
             odd = false;
+            if ((k0 & 255u) == 0 && P.bsum) {   // one sum per 256 samples
+                P.bsum[(U.f_off + ns + k0 - 256) >> 8] = fsum;
+                fsum = 0.0;
+            }
         }
         const bool quiet = (k0 + 8 <= count) && (time > 9.0f * dt) && (jph + 9.0f * jinc < 1.0f);
         if (quiet) { // no hand-over and no wrap inside these 8 samples: literal clocks, no event tests
@@ -397,7 +405,7 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
         }
     }
     P.fflags[(U.f_off + ns + ((count - 1) & ~127u)) >> 7] = odd ? 1u : 0u;   // the last (possibly partial) 128-block
-    if (P.bsum) P.bsum[(U.f_off + ns) >> 8] = fsum;
+    if (P.bsum) P.bsum[(U.f_off + ns + ((count - 1) & ~255u)) >> 8] = fsum;   // the last (possibly partial) 256-run
     if (it.n0 + it.len == U.n_samples && off + count == it.len) {
         // the lane that wrote the utterance's last sample rounds the row up: k_phase_pair copies F_t in groups of 8
         // and the flag words in pairs, so nothing it touches is left unwritten (the values themselves are unused)
@@ -1323,6 +1331,7 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
     const float quiet_t = 17.0f * dt, quiet_j = 1.0f - 17.0f * jinc;   // no hand-over / wrap within the next 16 samples
     const uint32_t jseed = U.voice.jitter_seed;
 
+    const bool has_init = U.has_init != 0u;     // a continued stream (read once: the loop below must not reload it)
     FormantLane L[FPT];
     bool on = false;
 #pragma unroll
@@ -1361,6 +1370,7 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
         const uint32_t t = wslot[0]; wslot[0] = wslot[FPT - 1]; wslot[FPT - 1] = t;
     }
     const uint32_t wmax = wslot[0];
+    const bool keep_slot1 = has_init && wslot[FPT - 1] >= it.n0;   // the second slot starts at the window's sample 0 with the carried state
     const int r_join = (FPT == 2) ? -(int)wslot[FPT - 1] : (int)0x80000000;   // first row of the second slot
     const uint32_t wmine = min(wmax, it.n0);      // multiple of 16 (n0 is a multiple of 256)
     const uint32_t ns = it.n0 - wmine;            // first sample this lane computes
@@ -1418,7 +1428,7 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
             // A continued stream: the Synthesize filter states carry over.  They apply to every slot whose run starts at
             // the window's sample 0 -- the first chunk, and any later chunk whose warm-up reaches back to sample 0 (there
             // a start from rest would ignore the carried state; its error decays only with the warm-up actually available).
-            if (U.has_init && wslot[j] >= it.n0) {
+            if (has_init && wslot[j] >= it.n0) {
                 const float* st0 = P.utt_init + (size_t)it.utt * 32;
                 L[j].a = st0[L[j].fi]; L[j].b = st0[8 + L[j].fi]; L[j].c = st0[16 + L[j].fi];
             }
@@ -1583,7 +1593,7 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
         if (FPT == 2 && r == r_join && r_join != -(int)wmax) {
             // the second slot starts here, from rest (whatever the exact / hand-over rows before may have left in it)
             // (... unless it starts at the window's sample 0 of a continued stream: it then holds the carried state)
-            if (act && !(U.has_init && wslot[FPT - 1] >= it.n0)) { L[FPT - 1].a = 0.f; L[FPT - 1].b = 0.f; L[FPT - 1].c = 0.f; }
+            if (act && !keep_slot1) { L[FPT - 1].a = 0.f; L[FPT - 1].b = 0.f; L[FPT - 1].c = 0.f; }
             c_valid = false;
         }
         if (act) {

@@ -735,7 +735,7 @@ __global__ void __launch_bounds__(32) k_phase_chain(PlanDev P, uint32_t round)
     }
 }
 
-__global__ void __launch_bounds__(256) k_phase_saw(PlanDev P, uint32_t round)
+__global__ void __launch_bounds__(512) k_phase_saw(PlanDev P, uint32_t round)
 {
     const uint32_t n_dirty = P.pstats[PSTAT_PENDING + round];
     if (n_dirty == 0u) return;

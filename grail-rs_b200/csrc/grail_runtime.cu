@@ -917,9 +917,10 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
     }
     CU(ctx, cudaEventRecord(ev[1], s));
     if (pl->n_items) {
-        const uint32_t runs = (pl->chunk_len + FREQ_RUN - 1) / FREQ_RUN;
+        const uint32_t run_len = pl->n_jscheds == 1 ? (uint32_t)FREQ_RUN_MAX : 256u;   // (see k_frequency)
+        const uint32_t runs = (pl->chunk_len + run_len - 1) / run_len;
         const uint64_t threads = (uint64_t)pl->n_groups * 32ull * runs;
-        k_frequency<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(P, runs);
+        k_frequency<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(P, runs, run_len);
         pl->last_launches++;
     }
     CU(ctx, cudaEventRecord(ev[2], s));
@@ -962,7 +963,7 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
         // worst case (every chunk dirty) and the CTAs past the list's end leave at once
         // repair rounds walk a dense list of dirty chunks whose length only the device knows: fixed grids stride over it
         const unsigned dgc = std::min<unsigned>((pl->n_pchunks + 31) / 32, (unsigned)ctx->prop.multiProcessorCount * 6u);
-        const dim3 dgs(std::max(1u, std::min(256u, (pl->n_pchunks + 2047u) / 2048u)), (pl->phase_chunk + 7u) / 8u);
+        const dim3 dgs(std::max(1u, std::min(128u, (pl->n_pchunks + 4095u) / 4096u)), (pl->phase_chunk + 7u) / 8u);
         k_phase_guess<<<wg, 128, 0, s>>>(P);
         pl->last_launches++;
         if (pl->max_pchunks > 1) {
@@ -981,7 +982,7 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
         for (int r = 1; r <= rounds; ++r) {
             k_phase_fix<<<wg, 128, 0, s>>>(P, (uint32_t)r);
             k_phase_chain<<<dgc, 32, 0, s>>>(P, (uint32_t)r);
-            k_phase_saw<<<dgs, 256, 0, s>>>(P, (uint32_t)r);   // (y: the blocks of a chunk)
+            k_phase_saw<<<dgs, 512, 0, s>>>(P, (uint32_t)r);   // (y: the blocks of a chunk)
             pl->last_launches += 3;
         }
         k_phase_fix<<<wg, 128, 0, s>>>(P, (uint32_t)PH_MAX_ROUNDS + 1u);   // the final proof: sets the status bits
