@@ -7,7 +7,7 @@ ctx = g.Context(0)
 stream = torch.cuda.ExternalStream(ctx.stream_handle)
 elems, offs, vp = W.config2(1024, 10)
 import itertools
-for pipe, tl, lean in [(0, 0, -1), (1, 0, -1), (1, 0, 1), (1, 14208, 1), (1, 18944, 1), (1, 14208, 0), (1, 23680, 1)]:
+for pipe, tl, lean in [(0, 0, -1), (1, 0, -1), (0, 23680, -1), (1, 23680, -1), (0, 18944, -1), (1, 18944, -1), (1, 14208, -1), (1, 21312, -1)]:
     if True:
         ctx.set_option("pipeline", pipe); ctx.set_option("target_lanes", tl); ctx.set_option("phase_lean", lean)
         plan = ctx.plan(elems, offs, vp)

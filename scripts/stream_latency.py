@@ -24,3 +24,27 @@ for window in (441, 4410, 44100):
     print(f"window {window:6d} samples ({window/44.1:.0f} ms of audio): {len(lat)} pulls, median {np.median(lat):.0f} us, p99 {np.percentile(lat, 99):.0f} us, "
           f"real-time factor {window/44100/np.median(lat)*1e6:.0f}")
     st.close() if hasattr(st, "close") else None
+
+# batched pulls (grail_cuda_streams_pull): N concurrent streams, one plan and one launch per kernel per tick
+print("batched pulls of a 10 ms window (441 samples per stream and tick):")
+for n in (1, 8, 64, 256, 1024):
+    streams = []
+    for k in range(n):
+        p = vp[0].copy()
+        p["jitter_seed"] = k
+        st = ctx.stream(p)
+        st.push(elems)
+        st.finish()
+        streams.append(st)
+    lat = []
+    for tick in range(60):
+        t0 = time.perf_counter()
+        xs = g.pull_streams(streams, 441)
+        lat.append(time.perf_counter() - t0)
+        if len(xs[0]) == 0:
+            break
+    lat = np.array(lat[2:]) * 1e6
+    print(f"  {n:5d} streams: median {np.median(lat):8.0f} us per tick = {np.median(lat) / n:7.1f} us per stream, "
+          f"{n * 441 / np.median(lat) * 1e6:.3e} samples/s aggregate, {n * 0.01 / np.median(lat) * 1e6:.0f} real-time streams per GPU")
+    for st in streams:
+        st.close()
