@@ -1578,8 +1578,12 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
     struct Coef2 { f2_t a1, g, lp, amp0, amp1, br, m1; };
     Coef2 p0 = { 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull }, pd = p0;   // packed block start / block delta (FPT = 2)
     bool hand = false, warp_exact = false;
-    int half = 0;
-    for (int r = -(int)wmax; r < (int)lmax; r += 8, half ^= 1) {
+    // (two halves per trip, unrolled: `half` is a constant in each copy and the saw double buffer alternates between two
+    //  register sets instead of being copied every 8 samples; wmax and lmax are multiples of 16)
+    for (int r0 = -(int)wmax; r0 < (int)lmax; r0 += 16) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int r = r0 + half * 8;
         const bool act = r >= r_lo && r < r_hi;
         const float4 sa = na, sb = nb;
         if (r + 8 >= r_lo && r + 8 < r_hi) fetch();
@@ -1732,21 +1736,13 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
                 if (FPT == 2 && r >= r_join) interp_block2();
                 else if (FPT == 1) interp_block(std::integral_constant<int, FPT>{});
                 else interp_block(std::integral_constant<int, 1>{});
-            } else if (!hand) {
-                // a kink somewhere in the warp: exact coefficients every sample, one inlined wrap test per sample
-                const float s8[8] = { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w };
-                c_valid = false;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    v[k] = sample(s8[k]);
-                    time = __fadd_rn(time, ndt);                             // :861
-                    jph = __fadd_rn(jph, jinc);                              // :291
-                    if (__builtin_expect(jph > 1.0f, 0)) jitter_wrap();      // :294
-                }
             } else {
-                // the phoneme's last samples: generic per-sample loop (results parked in the smem row)
+                // a kink somewhere in the warp (exact coefficients every sample) or the phoneme's / the chunk's last
+                // samples: ONE generic per-sample loop, rolled (results parked in the smem row) -- its code is a tenth of
+                // the straight-line version's, which matters more than its loop overhead once many lanes of a warp have
+                // kinks of their own (per-utterance voices): the kernel's hot paths then fit the instruction cache
                 c_valid = false;
-                const int cnt = min(8, r_hi - r);
+                const int cnt = hand ? min(8, r_hi - r) : 8;
 #pragma unroll 1
                 for (int k = 0; k < cnt; ++k) {
                     const float4 q = k < 4 ? sa : sb;
@@ -1772,7 +1768,7 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
         if (r >= 0) {
             sts128(part_a + (r & (KT - 1)) * 4, v[0], v[1], v[2], v[3]);
             sts128(part_a + (r & (KT - 1)) * 4 + 16, v[4], v[5], v[6], v[7]);
-            if ((r & (KT - 1)) == KT - 8) {
+            if (half == 1 && (r0 & (KT - 1)) == KT - 16) {       // (r & (KT - 1)) == KT - 8
                 const uint32_t base = (uint32_t)r - (uint32_t)(KT - 8);
                 const uint32_t kb = base / (uint32_t)KT, slot = kb & 1u, use = kb >> 1;   // (RING) batch, its tile, the tile's n-th use
                 bool reduce_here = true;
@@ -1796,8 +1792,41 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
                 // 8 lanes per row, 4 rows per pass: sum the formant groups in index order (Array::sum, :123),
                 // scale (:574), store 16 bytes per lane = 128 contiguous bytes per row
                 const int sub = lane >> 3, l8 = lane & 7;
+                // The common case -- mono f32, no ring: the passes unrolled (a compile-time trip count), so that their row
+                // addresses differ by immediates instead of being rebuilt from the thread index in every pass.
+                constexpr int RED_PASSES = (32 * (KT / 32) + NW * 4 - 1) / (NW * 4);
+                const bool plain_out = !RING && P.out_channels == 1u && format == GRAIL_F32;
+                if (plain_out) {
+#pragma unroll
+                    for (int i = 0; i < RED_PASSES; ++i) {
+                        const int rc = w * 4 + sub + i * NW * 4;
+                        if (rc >= 32 * (KT / 32)) break;
+                        const int row = rc & 31, cb = (rc >> 5) * 32;
+                        const uint32_t rl = row_len[row];
+                        const uint32_t s0 = base + cb + l8 * 4;
+                        if (s0 < rl) {
+                            float4 acc = *reinterpret_cast<const float4*>(&part[0][row][cb + l8 * 4]);
+#pragma unroll
+                            for (int f = 1; f < NW; ++f) {
+                                const float4 t = *reinterpret_cast<const float4*>(&part[f][row][cb + l8 * 4]);
+                                acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+                            }
+                            acc.x *= 0.5f; acc.y *= 0.5f; acc.z *= 0.5f; acc.w *= 0.5f;
+                            float* op = reinterpret_cast<float*>(out) + (row_out[row] + s0);
+                            const uint32_t cnt = rl - s0;
+                            if (cnt >= 4u && (reinterpret_cast<uintptr_t>(op) & 15u) == 0) {
+                                *reinterpret_cast<float4*>(op) = acc;
+                            } else {
+                                const float a4[4] = { acc.x, acc.y, acc.z, acc.w };
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    if ((uint32_t)q < cnt) op[q] = a4[q];
+                            }
+                        }
+                    }
+                }
 #pragma unroll 1
-                for (int rc = rc0 + sub; reduce_here && rc < 32 * (KT / 32); rc += rcs) {
+                for (int rc = rc0 + sub; !plain_out && reduce_here && rc < 32 * (KT / 32); rc += rcs) {
                     const int row = rc & 31, cb = (rc >> 5) * 32;          // (row, 32-sample column block) of the tile
                     const uint32_t rl = row_len[row];
                     const uint32_t s0 = base + cb + l8 * 4;
@@ -1856,6 +1885,7 @@ k_formant(PlanDev P, void* __restrict__ out, int format)
                 }
             }
         }
+      }
     }
     // the lane that owns an utterance's last chunk leaves the Synthesize filter states behind (stream state)
     if (on && it.n0 + it.len == U.n_samples) {
