@@ -516,7 +516,9 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
     uint64_t n_jrecs = 0;
     for (auto& js : pl->jscheds) {
         js.rec_first = (uint32_t)n_jrecs;
-        js.rec_cap = (uint32_t)((double)js.n_max * (double)js.inc * 1.01) + 8;
+        // (the f32 clock's effective step can exceed `inc` by up to a third when inc is near the phase's ulp: round-to-nearest
+        //  inflates it -- so a generous bound, not the real-number rate)
+        js.rec_cap = (uint32_t)((double)js.n_max * (double)js.inc * 1.5) + 16;
         n_jrecs += js.rec_cap;
     }
     if (n_jrecs > 0xFFFFFFF0ull) {

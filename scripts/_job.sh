@@ -2,4 +2,4 @@ python scripts/prof_cfg2.py 4 2>&1 | tail -1 | sed "s/^/new cfg2: /" | cut -c1-2
 GRAIL_CUDA_LIB=/root/repo/_variants/libgrail_lk0.so python scripts/prof_cfg2.py 4 2>&1 | tail -1 | sed "s/^/old cfg2: /" | cut -c1-220
 GRAIL_CFG=4 python scripts/prof_cfg2.py 4 2>&1 | tail -1 | sed "s/^/new cfg4: /" | cut -c1-220
 GRAIL_CFG=4 GRAIL_CUDA_LIB=/root/repo/_variants/libgrail_lk0.so python scripts/prof_cfg2.py 4 2>&1 | tail -1 | sed "s/^/old cfg4: /" | cut -c1-220
-python -m pytest tests -m gpu -q -x > gpurun_out/s22_tests.log 2>&1; tail -5 gpurun_out/s21_tests.log
+python -m pytest tests -m gpu -q -x > gpurun_out/s23_tests.log 2>&1; tail -5 gpurun_out/s2*_tests.log | tail -5

@@ -88,8 +88,10 @@ def test_stream_multi_chunk_window_narrow_bandwidth(ctx, oracle):
     got = np.concatenate(got)
     st.close()
     assert len(got) == len(want)
-    # the stream against the one-shot rendering on the same arithmetic: the carried state, nothing else, is under test
-    assert float(np.abs(got - one_shot).max()) <= 5e-6, float(np.abs(got - one_shot).max())
+    # the stream against the one-shot rendering: the carried state is under test (a start from rest is off by 1e-2 here).
+    # The two renderings chunk the utterance differently, so their 8 / 16-sample interpolation blocks differ and this
+    # high-Q voice shows it at rounding level (measured 5.2e-6).
+    assert float(np.abs(got - one_shot).max()) <= 1e-5, float(np.abs(got - one_shot).max())
     stats = W.parity_stats(got, want)
     print(stats)
     assert stats["max_abs"] <= 1e-4 and stats["snr_db"] >= 90.0, stats
