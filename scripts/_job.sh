@@ -1,5 +1,9 @@
-python scripts/prof_cfg2.py 4 2>&1 | tail -1 | sed "s/^/new cfg2: /" | cut -c1-220
-GRAIL_CUDA_LIB=/root/repo/_variants/libgrail_lk0.so python scripts/prof_cfg2.py 4 2>&1 | tail -1 | sed "s/^/old cfg2: /" | cut -c1-220
-GRAIL_CFG=4 python scripts/prof_cfg2.py 4 2>&1 | tail -1 | sed "s/^/new cfg4: /" | cut -c1-220
-GRAIL_CFG=4 GRAIL_CUDA_LIB=/root/repo/_variants/libgrail_lk0.so python scripts/prof_cfg2.py 4 2>&1 | tail -1 | sed "s/^/old cfg4: /" | cut -c1-220
-python -m pytest tests -m gpu -q -x > gpurun_out/s23_tests.log 2>&1; tail -5 gpurun_out/s2*_tests.log | tail -5
+set -x
+O=gpurun_out
+python bench.py --impl reference > $O/f1_ref_c2.json 2> $O/f1_ref_c2.err
+python bench.py > $O/f1_c2_n1.json 2> $O/f1_c2_n1.err
+python bench.py --pipeline 0 > $O/f1_c2_n1_inorder.json 2> /dev/null
+python bench.py --config 3 --steps 10 > $O/f1_c3_n1.json 2> $O/f1_c3_n1.err
+python bench.py --config 4 --steps 5 > $O/f1_c4_n1.json 2> $O/f1_c4_n1.err
+python bench.py --config 5 --steps 5 > $O/f1_c5_n1.json 2> $O/f1_c5_n1.err
+for f in $O/f1_*.json; do echo == $f; head -c 400 $f; echo; done
