@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <string>
@@ -57,6 +58,11 @@ struct grail_ctx {
     cudaStream_t   s_copy = nullptr;    // one-shot batches: device-to-host copies of finished utterance groups
     int      e2e_groups = -1;        // one-shot batches: utterance groups whose copies overlap the next group's kernels (-1 auto)
     std::vector<grail_plan*> live_plans;   // plans created on this ctx and not yet destroyed (synchronize clears their in_flight)
+    // Plan uploads: the host-built tables go through pinned staging blocks on their own stream, so building the next
+    // plan neither waits for the kernels already queued on `stream` (a copy from pageable memory synchronises the
+    // stream it is issued on) nor delays them.
+    cudaStream_t   s_up = nullptr;
+    std::vector<PoolBuf> hpool;            // pinned host blocks, reused across plans
 };
 
 static int set_err(grail_ctx* ctx, int status, const char* fmt, ...)
@@ -122,10 +128,36 @@ static void pool_free(grail_ctx* ctx, void* p)
         if (b.ptr == p) { b.in_use = false; return; }
 }
 
+// pinned host staging blocks (same discipline as the device pool: smallest free block that fits, else a new one)
+static int hpool_alloc(grail_ctx* ctx, size_t bytes, void** out)
+{
+    bytes = (bytes + 0xFFFFFull) & ~0xFFFFFull;          // whole MiB
+    PoolBuf* best = nullptr;
+    for (auto& b : ctx->hpool)
+        if (!b.in_use && b.size >= bytes && (!best || b.size < best->size)) best = &b;
+    if (best) { best->in_use = true; *out = best->ptr; return GRAIL_OK; }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(ctx, GRAIL_ERR_OOM, "cudaHostAlloc(%zu) for plan staging failed", bytes);
+    }
+    ctx->hpool.push_back(PoolBuf{ p, bytes, true });
+    *out = p;
+    return GRAIL_OK;
+}
+static void hpool_free(grail_ctx* ctx, void* p)
+{
+    if (!p) return;
+    for (auto& b : ctx->hpool)
+        if (b.ptr == p) { b.in_use = false; return; }
+}
+
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
 struct grail_plan {
+    void*       h_stage = nullptr;      // pinned staging block of this plan's uploads (back to the ctx's pool with the plan)
+    cudaEvent_t ev_up = nullptr;        // uploads done (the main stream waits on it)
     grail_ctx* ctx = nullptr;
     uint32_t n_utts = 0, n_elems = 0, n_items = 0, n_groups = 0, n_jscheds = 0, n_jrecs = 0, nw = 1, fpt = 1;
     uint32_t chunk_len = 0;
@@ -413,6 +445,8 @@ static void plan_release(grail_plan* pl)
         for (auto& e : sl.ev) if (e) cudaEventDestroy(e);
     }
     if (pl->ev_begin) cudaEventDestroy(pl->ev_begin);
+    if (pl->ev_up) { cudaEventSynchronize(pl->ev_up); cudaEventDestroy(pl->ev_up); }   // (the staging block is free to reuse after this)
+    hpool_free(ctx, pl->h_stage);
     pool_free(ctx, pl->d_pscan_status);
     for (auto& e : pl->ev)
         if (e) cudaEventDestroy(e);
@@ -437,6 +471,12 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
     pl->segs.resize(pl->n_elems ? pl->n_elems : 1);
     pl->out_offsets.assign(n_utts + 1, 0);
 
+    static const bool ptrace = getenv("GRAIL_PLAN_TRACE") != nullptr;
+    const auto pt0 = std::chrono::steady_clock::now();
+    auto pmark = [&](const char* what) {
+        if (ptrace) fprintf(stderr, "[grail plan] %-28s at %.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - pt0).count());
+    };
+    pmark("validated");
     // ---- exact schedule + active formants
     SeqCache cache;
     std::unordered_map<uint64_t, uint32_t> jmap;
@@ -541,6 +581,7 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
         }
     }
 
+    pmark("schedule + active formants");
     // ---- chunking: aim for one resident wave of k_formant CTAs (32 chunks each)
     uint64_t target = ctx->target_items;
     if (target == 0) {
@@ -580,6 +621,7 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
     cl = std::min<uint64_t>(cl, cl_hi);
     pl->chunk_len = (uint32_t)cl;
 
+    pmark("chunk length");
     // ---- work items: utterances in descending length so a CTA's 32 chunks are of similar size
     std::vector<uint32_t> order(n_utts);
     for (uint32_t u = 0; u < n_utts; ++u) order[u] = u;
@@ -630,6 +672,7 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
     pl->n_groups = (pl->n_items + 31) / 32;
     pl->saw_words = (uint64_t)pl->n_groups * 32ull * pl->chunk_len;
 
+    pmark("work items");
     // ---- chunk-parallel exact phase (grail_phase.cuh): every work item is cut into K phase chunks of PC samples, a
     //      multiple of 256; an utterance's chunks are numbered in time order.  PC "auto": enough chunks for about 16
     //      warps of walks per SM (the walks are streaming kernels), at least 1024 samples (a chunk without a carrier
@@ -731,6 +774,7 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
         }
     }
 
+    pmark("phase chunks");
     // ---- device buffers
     auto fail = [&](int code) { plan_release(pl); return code; };
 #define PA(ptr, bytes)                                                         \
@@ -798,10 +842,36 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
         pl->pscans.push_back(S);
     }
     cudaStream_t s = ctx->stream;
-    if (pl->n_elems && in.full)
-        CUF(cudaMemcpyAsync(pl->d_elems, in.full, (size_t)pl->n_elems * sizeof(grail_seq_elem), cudaMemcpyHostToDevice, s));
-    CUF(cudaMemcpyAsync(pl->d_segs, pl->segs.data(), pl->segs.size() * sizeof(SegRec), cudaMemcpyHostToDevice, s));
-    if (n_utts) CUF(cudaMemcpyAsync(pl->d_utts, pl->utts.data(), n_utts * sizeof(UttDev), cudaMemcpyHostToDevice, s));
+    // Uploads: one pinned staging block per plan, filled here, copied on the upload stream; the main stream waits on
+    // an event.  Nothing in this function waits for work already queued on the main stream.
+    const bool staged = !in.phoneme_level();
+    size_t stage_bytes = 0;
+    auto stage_room = [&](size_t bytes) { const size_t o = stage_bytes; stage_bytes += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t so_elems = stage_room((size_t)pl->n_elems * sizeof(grail_seq_elem));
+    const size_t so_segs = stage_room(pl->segs.size() * sizeof(SegRec));
+    const size_t so_utts = stage_room((size_t)n_utts * sizeof(UttDev));
+    const size_t so_items = stage_room((size_t)pl->n_items * sizeof(ItemDev));
+    const size_t so_js = stage_room((size_t)pl->n_jscheds * sizeof(JitSchedDev));
+    const size_t so_jr = stage_room((size_t)pl->n_jrecs * sizeof(JitRec));
+    const size_t so_init = stage_room(init_states.size() * sizeof(float));
+    cudaStream_t su = staged ? ctx->s_up : s;
+    char* hs = nullptr;
+    if (staged) {
+        void* hp = nullptr;
+        int rch = hpool_alloc(ctx, stage_bytes + 256, &hp);
+        if (rch) return fail(rch);
+        pl->h_stage = hp;
+        hs = (char*)hp;
+    }
+    auto upload = [&](void* dst, const void* src, size_t bytes, size_t off) -> cudaError_t {
+        if (!bytes) return cudaSuccess;
+        if (!staged) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
+        memcpy(hs + off, src, bytes);
+        return cudaMemcpyAsync(dst, hs + off, bytes, cudaMemcpyHostToDevice, su);
+    };
+    if (pl->n_elems && in.full) CUF(upload(pl->d_elems, in.full, (size_t)pl->n_elems * sizeof(grail_seq_elem), so_elems));
+    CUF(upload(pl->d_segs, pl->segs.data(), pl->segs.size() * sizeof(SegRec), so_segs));
+    if (n_utts) CUF(upload(pl->d_utts, pl->utts.data(), n_utts * sizeof(UttDev), so_utts));
     if (pl->n_elems && in.phoneme_level()) {
         // Selector (and, for bare ids, the Intonator stub) on the device: 1-16 bytes per phoneme cross PCIe instead of 208
         SelectDev S;
@@ -832,17 +902,26 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
         CUF(cudaGetLastError());
         pl->select_on_device = true;
     }
-    if (pl->n_items) CUF(cudaMemcpyAsync(pl->d_items, pl->items.data(), pl->n_items * sizeof(ItemDev), cudaMemcpyHostToDevice, s));
-    if (pl->n_jscheds) CUF(cudaMemcpyAsync(pl->d_jscheds, pl->jscheds.data(), pl->n_jscheds * sizeof(JitSchedDev), cudaMemcpyHostToDevice, s));
-    if (pl->jit_on_host && pl->n_jrecs) CUF(cudaMemcpyAsync(pl->d_jrecs, pl->jrecs.data(), (size_t)pl->n_jrecs * sizeof(JitRec), cudaMemcpyHostToDevice, s));
+    if (pl->n_items) CUF(upload(pl->d_items, pl->items.data(), pl->n_items * sizeof(ItemDev), so_items));
+    if (pl->n_jscheds) CUF(upload(pl->d_jscheds, pl->jscheds.data(), pl->n_jscheds * sizeof(JitSchedDev), so_js));
+    if (pl->jit_on_host && pl->n_jrecs) CUF(upload(pl->d_jrecs, pl->jrecs.data(), (size_t)pl->n_jrecs * sizeof(JitRec), so_jr));
     {
-        CUF(cudaMemsetAsync(pl->d_utt_init, 0, std::max<size_t>(n_utts, 1) * 32 * sizeof(float), s));
-        CUF(cudaMemsetAsync(pl->d_utt_final, 0, std::max<size_t>(n_utts, 1) * 32 * sizeof(float), s));
-        CUF(cudaMemsetAsync(pl->d_utt_status, 0, std::max<size_t>(n_utts, 1) * sizeof(uint32_t), s));
-        CUF(cudaMemsetAsync(pl->d_pstats, 0, 256, s));
+        // (these buffers come from the pool: whatever used them before was queued on `stream` or has been drained, and
+        //  the upload stream is ordered before `stream` below -- so the memsets go first on the stream that writes them)
+        CUF(cudaMemsetAsync(pl->d_utt_init, 0, std::max<size_t>(n_utts, 1) * 32 * sizeof(float), su));
+        CUF(cudaMemsetAsync(pl->d_utt_final, 0, std::max<size_t>(n_utts, 1) * 32 * sizeof(float), su));
+        CUF(cudaMemsetAsync(pl->d_utt_status, 0, std::max<size_t>(n_utts, 1) * sizeof(uint32_t), su));
+        CUF(cudaMemsetAsync(pl->d_pstats, 0, 256, su));
         if (ss) {   // formants nobody touches in this window keep their carried state
-            CUF(cudaMemcpyAsync(pl->d_utt_init, init_states.data(), init_states.size() * sizeof(float), cudaMemcpyHostToDevice, s));
-            CUF(cudaMemcpyAsync(pl->d_utt_final, init_states.data(), init_states.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+            const size_t ib = init_states.size() * sizeof(float);
+            if (staged) {
+                memcpy(hs + so_init, init_states.data(), ib);
+                CUF(cudaMemcpyAsync(pl->d_utt_init, hs + so_init, ib, cudaMemcpyHostToDevice, su));
+                CUF(cudaMemcpyAsync(pl->d_utt_final, hs + so_init, ib, cudaMemcpyHostToDevice, su));
+            } else {
+                CUF(cudaMemcpyAsync(pl->d_utt_init, init_states.data(), ib, cudaMemcpyHostToDevice, s));
+                CUF(cudaMemcpyAsync(pl->d_utt_final, init_states.data(), ib, cudaMemcpyHostToDevice, s));
+            }
         }
     }
     for (auto& e : pl->ev) CUF(cudaEventCreate(&e));
@@ -858,8 +937,15 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
             for (auto& e : sl.ev) CUF(cudaEventCreate(&e));
         }
     }
-    // the host vectors are read by the async copies above: make them safe to outlive this call
-    CUF(cudaStreamSynchronize(s));
+    if (staged) {
+        // the copies read the plan's own pinned block: nothing to wait for here; the kernels wait on the device
+        CUF(cudaEventCreateWithFlags(&pl->ev_up, cudaEventDisableTiming));
+        CUF(cudaEventRecord(pl->ev_up, su));
+        CUF(cudaStreamWaitEvent(s, pl->ev_up, 0));
+    } else {
+        // (phoneme-level input) the host vectors are read by the async copies above: make them safe to outlive this call
+        CUF(cudaStreamSynchronize(s));
+    }
 #undef PA
 #undef CUF
     ctx->live_plans.push_back(pl);
@@ -1083,7 +1169,8 @@ int grail_cuda_create(int device, grail_ctx** out_ctx)
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithPriority(&ctx->s_front, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
         cudaStreamCreateWithPriority(&ctx->s_back, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->s_up, cudaStreamNonBlocking) != cudaSuccess) {
         cudaGetLastError();
         grail_cuda_destroy(ctx);             // destroys whichever streams were created
         return GRAIL_ERR_CUDA;
@@ -1105,8 +1192,11 @@ void grail_cuda_destroy(grail_ctx* ctx)
     if (ctx->s_front) { cudaStreamSynchronize(ctx->s_front); cudaStreamDestroy(ctx->s_front); }
     if (ctx->s_back) { cudaStreamSynchronize(ctx->s_back); cudaStreamDestroy(ctx->s_back); }
     if (ctx->s_copy) { cudaStreamSynchronize(ctx->s_copy); cudaStreamDestroy(ctx->s_copy); }
+    if (ctx->s_up) { cudaStreamSynchronize(ctx->s_up); cudaStreamDestroy(ctx->s_up); }
     for (auto& b : ctx->pool)
         if (b.ptr) cudaFree(b.ptr);
+    for (auto& b : ctx->hpool)
+        if (b.ptr) cudaFreeHost(b.ptr);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     cudaGetLastError();
     delete ctx;
@@ -1123,6 +1213,7 @@ int grail_cuda_synchronize(grail_ctx* ctx)
     CU(ctx, cudaStreamSynchronize(ctx->s_front));
     CU(ctx, cudaStreamSynchronize(ctx->s_back));
     CU(ctx, cudaStreamSynchronize(ctx->s_copy));
+    CU(ctx, cudaStreamSynchronize(ctx->s_up));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     // everything has drained: the next pipelined launch of any plan is again "the first of a burst" and orders itself
     // after whatever the caller queues on the main stream from now on
@@ -1506,6 +1597,15 @@ static int synthesize_batch_impl(grail_ctx* ctx, const grail_seq_elem* elems, co
     std::vector<cudaEvent_t> done;
     std::vector<uint32_t> offs;
     int rc = GRAIL_OK;
+    // GRAIL_E2E_TRACE=1: per-group timeline on stderr (host time at enqueue; device times of kernels-done and copy-done)
+    static const bool trace = getenv("GRAIL_E2E_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    std::vector<double> thost;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+    if (trace) {
+        cudaEvent_t e0; cudaEventCreate(&e0); cudaEventRecord(e0, ctx->stream); tev.push_back(e0);
+    }
     for (size_t g = 0; g + 1 < bounds.size() && !rc; ++g) {
         const uint32_t u0 = bounds[g], u1 = bounds[g + 1], nu = u1 - u0;
         offs.resize(nu + 1);
@@ -1540,6 +1640,11 @@ static int synthesize_batch_impl(grail_ctx* ctx, const grail_seq_elem* elems, co
                 if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_copy, ev, 0);
                 if (e == cudaSuccess)
                     e = cudaMemcpyAsync(gbase, d, (size_t)pl->total_samples * eb, cudaMemcpyDeviceToHost, ctx->s_copy);
+                if (trace) {
+                    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+                    cudaEventRecord(a, ctx->stream); cudaEventRecord(b, ctx->s_copy);
+                    tev.push_back(a); tev.push_back(b); thost.push_back(host_ms());
+                }
                 if (e != cudaSuccess) rc = set_err(ctx, GRAIL_ERR_CUDA, "device-to-host copy failed: %s", cudaGetErrorString(e));
             }
         }
@@ -1549,6 +1654,18 @@ static int synthesize_batch_impl(grail_ctx* ctx, const grail_seq_elem* elems, co
     cudaError_t ec = cudaStreamSynchronize(ctx->s_copy);
     if (!rc && (es != cudaSuccess || ec != cudaSuccess))
         rc = set_err(ctx, GRAIL_ERR_CUDA, "one-shot batch failed: %s", cudaGetErrorString(es != cudaSuccess ? es : ec));
+    if (trace && !tev.empty()) {
+        const double t_sync = host_ms();
+        for (size_t g = 0; 2 * g + 2 < tev.size(); ++g) {
+            float k = 0.f, c = 0.f;
+            cudaEventElapsedTime(&k, tev[0], tev[2 * g + 1]);
+            cudaEventElapsedTime(&c, tev[0], tev[2 * g + 2]);
+            fprintf(stderr, "[grail e2e] group %zu (%u utts): enqueued at host %.2f ms, kernels done at %.2f ms, copy done at %.2f ms\n", g,
+                    bounds[g + 1] - bounds[g], thost[g], k, c);
+        }
+        fprintf(stderr, "[grail e2e] drained at host %.2f ms\n", t_sync);
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    }
     for (grail_plan* pl : plans) {
         if (!rc) rc = plan_check_device_errors(pl);
         plan_release(pl);
