@@ -257,13 +257,20 @@ __device__ __forceinline__ void walk_blocks(unsigned char* ring, const float* __
 // ------------------------------------------------------------------------------------------------
 // guesses: phase before each chunk = init + sum of F_t (mod 1), from the per-run sums.  One warp per utterance.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_phase_guess(PlanDev P)
+// WPU = warps per utterance: 1 (four utterances per CTA of 128 lanes: seconds of speech, hundreds of chunks) or 32 (one
+// CTA of 1024 lanes per utterance: long forms, tens of thousands of chunks -- a lone warp would loop over them 32 at a
+// time, a dependent global load per trip).  The CTA-wide scans are the warp scan, the warps' totals scanned by warp 0.
+template <int WPU>
+__global__ void __launch_bounds__(WPU == 1 ? 128 : 32 * WPU) k_phase_guess(PlanDev P)
 {
-    const uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    constexpr bool CTA = WPU > 1;
+    constexpr uint32_t TILE = 32u * (uint32_t)WPU;
+    __shared__ double sh_d[CTA ? 2 * WPU + 1 : 1];
+    const uint32_t u = CTA ? blockIdx.x : (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, w = CTA ? (int)(threadIdx.x >> 5) : 0;
     if (u >= P.n_utts) return;
     const UttDev& U = P.utts[u];
-    if (lane == 0) P.utt_status[u] = 0u;
+    if (lane == 0 && w == 0) P.utt_status[u] = 0u;
     const uint32_t C = U.pc_count, PC = P.phase_chunk, K = P.pc_per_item, CL = P.chunk_len;
     if (C == 0) return;
     float* start = pcf(P, PCF_START) + U.pc_first;
@@ -281,11 +288,11 @@ __global__ void __launch_bounds__(128) k_phase_guess(PlanDev P)
         return s;
     };
     double carry = (double)U.init_phase;
-    double s_next = chunk_sum(lane);
-    for (uint32_t c0 = 0; c0 < C; c0 += 32) {
-        const uint32_t c = c0 + lane;
+    double s_next = chunk_sum((uint32_t)w * 32u + lane);
+    for (uint32_t c0 = 0; c0 < C; c0 += TILE) {
+        const uint32_t c = c0 + (uint32_t)w * 32u + lane;
         const double s = s_next;
-        s_next = chunk_sum(c + 32);                // the next block's loads fly during this block's scan
+        s_next = chunk_sum(c + TILE);              // the next block's loads fly during this block's scan
         double incl = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -294,13 +301,34 @@ __global__ void __launch_bounds__(128) k_phase_guess(PlanDev P)
         }
         double excl = __shfl_up_sync(0xffffffffu, incl, 1);
         if (lane == 0) excl = 0.0;
+        double tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (CTA) {
+            if (lane == 31) sh_d[w] = incl;
+            __syncthreads();
+            if (w == 0) {
+                double a = lane < WPU ? sh_d[lane] : 0.0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double t = __shfl_up_sync(0xffffffffu, a, o);
+                    if (lane >= o) a = frac_d(a + t);
+                }
+                double ae = __shfl_up_sync(0xffffffffu, a, 1);
+                if (lane == 0) ae = 0.0;
+                if (lane < WPU) sh_d[WPU + lane] = ae;
+                if (lane == 31) sh_d[2 * WPU] = a;
+            }
+            __syncthreads();
+            excl = frac_d(sh_d[WPU + w] + excl);
+            tot = sh_d[2 * WPU];
+        }
         if (c < C) {
             float gph = (c == 0) ? U.init_phase : (float)frac_d(carry + excl);
             if (c != 0 && !(gph < 1.0f)) gph = 0.0f;           // 0.99999999 rounds to 1.0f
             start[c] = gph;
             flags[c] = (int32_t)PCH_DIRTY;
         }
-        carry = frac_d(carry + __shfl_sync(0xffffffffu, incl, 31));
+        carry = frac_d(carry + tot);
+        if (CTA) __syncthreads();                  // sh_d is written again in the next trip
     }
 }
 
@@ -453,10 +481,51 @@ __device__ __forceinline__ int parmap_block_scan(const ParMap& m, int lane, int&
     return mine;
 }
 
-__global__ void __launch_bounds__(128) k_phase_scan_a(PlanDev P)
+// the same over a CTA of WPU warps (sh: 2 * WPU + 1 maps of shared memory; every lane of the CTA must call it)
+template <int WPU>
+__device__ __forceinline__ int parmap_cta_scan(const ParMap& m, int lane, int w, int& kin, ParMap* sh)
 {
-    const uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    if (WPU == 1) return parmap_block_scan(m, lane, kin);
+    ParMap incl = m;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const ParMap t = parmap_shfl_up(incl, o);
+        if (lane >= o) incl = parmap_compose(t, incl);
+    }
+    ParMap excl = parmap_shfl_up(incl, 1);
+    if (lane == 0) { excl.e = 0; excl.o = 0; excl.is_const = 0; }
+    if (lane == 31) sh[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        ParMap a;
+        a.e = 0; a.o = 0; a.is_const = 0;
+        if (lane < WPU) a = sh[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const ParMap t = parmap_shfl_up(a, o);
+            if (lane >= o) a = parmap_compose(t, a);
+        }
+        ParMap ae = parmap_shfl_up(a, 1);
+        if (lane == 0) { ae.e = 0; ae.o = 0; ae.is_const = 0; }
+        if (lane < WPU) sh[WPU + lane] = ae;
+        if (lane == 31) sh[2 * WPU] = a;
+    }
+    __syncthreads();
+    const ParMap pre = sh[WPU + w], tot = sh[2 * WPU];
+    const int mine = parmap_apply(excl, parmap_apply(pre, kin));
+    kin = parmap_apply(tot, kin);
+    __syncthreads();                               // sh is written again by the next call
+    return mine;
+}
+
+template <int WPU>
+__global__ void __launch_bounds__(WPU == 1 ? 128 : 32 * WPU) k_phase_scan_a(PlanDev P)
+{
+    constexpr bool CTA = WPU > 1;
+    constexpr uint32_t TILE = 32u * (uint32_t)WPU;
+    __shared__ ParMap sh_m[CTA ? 2 * WPU + 1 : 1];
+    const uint32_t u = CTA ? blockIdx.x : (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, w = CTA ? (int)(threadIdx.x >> 5) : 0;
     if (u >= P.n_utts) return;
     const UttDev& U = P.utts[u];
     const uint32_t C = U.pc_count;
@@ -476,13 +545,13 @@ __global__ void __launch_bounds__(128) k_phase_scan_a(PlanDev P)
         }
         return x;
     };
-    int kin = 0;                                  // kc of the first chunk of this block of 32 (chunk 0: exact, 0)
-    In nx = load(lane);
-    for (uint32_t c0 = 0; c0 + 1 < C; c0 += 32) {
-        const uint32_t c = c0 + lane;
+    int kin = 0;                                  // kc of the first chunk of this block of TILE (chunk 0: exact, 0)
+    In nx = load((uint32_t)w * 32u + lane);
+    for (uint32_t c0 = 0; c0 + 1 < C; c0 += TILE) {
+        const uint32_t c = c0 + (uint32_t)w * 32u + lane;
         const bool valid = c + 1 < C;
         const In x = nx;
-        nx = load(c + 32);
+        nx = load(c + TILE);
         ParMap m;
         m.e = 0; m.o = 0; m.is_const = 0;         // identity for the padding lanes
         const bool anchored = (c == 0) || x.a >= 0;
@@ -494,7 +563,7 @@ __global__ void __launch_bounds__(128) k_phase_scan_a(PlanDev P)
             if (c == 0 || !anchored) { m.is_const = 1; m.e = m.o = D0; }   // chunk 0 is exact (kc = 0, trajectory 0)
             else { m.e = D0; m.o = D1 - 1; }
         }
-        const int kc = parmap_block_scan(m, lane, kin);   // this chunk's own offset
+        const int kc = parmap_cta_scan<WPU>(m, lane, w, kin, sh_m);   // this chunk's own offset
         if (valid) {
             int j = 0, base = 0;
             if (c != 0 && anchored) { j = kc & 1; base = kc - j; }
@@ -785,10 +854,14 @@ __global__ void __launch_bounds__(512) k_phase_saw(PlanDev P, uint32_t round)
 //   nothing about what follows: the chain restarts there with 0.  Chunks whose start changed are dirty and are
 //   walked again by the k_phase_b that follows; a round that finds every phi = 0 has proven the utterance.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_phase_fix(PlanDev P, uint32_t round /* the k_phase_b round that follows */)
+template <int WPU>
+__global__ void __launch_bounds__(WPU == 1 ? 128 : 32 * WPU) k_phase_fix(PlanDev P, uint32_t round /* the k_phase_b round that follows */)
 {
-    const uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    constexpr bool CTA = WPU > 1;
+    constexpr uint32_t TILE = 32u * (uint32_t)WPU;
+    __shared__ ParMap sh_m[CTA ? 2 * WPU + 1 : 1];
+    const uint32_t u = CTA ? blockIdx.x : (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, w = CTA ? (int)(threadIdx.x >> 5) : 0;
     if (u >= P.n_utts) return;
     if (P.utt_status[u] & 1u) return;
     const UttDev& U = P.utts[u];
@@ -811,12 +884,12 @@ __global__ void __launch_bounds__(128) k_phase_fix(PlanDev P, uint32_t round /* 
         }
         return x;
     };
-    In nx = load(lane);
-    for (uint32_t c0 = 0; c0 + 1 < C; c0 += 32) {
-        const uint32_t c = c0 + lane;
+    In nx = load((uint32_t)w * 32u + lane);
+    for (uint32_t c0 = 0; c0 + 1 < C; c0 += TILE) {
+        const uint32_t c = c0 + (uint32_t)w * 32u + lane;
         const bool valid = c + 1 < C;
         const In x = nx;
-        nx = load(c + 32);
+        nx = load(c + TILE);
         double phi = 0.0;
         bool bad = false, lat = true, hard = false;
         const float e = x.e, s = x.s;
@@ -839,7 +912,7 @@ __global__ void __launch_bounds__(128) k_phase_fix(PlanDev P, uint32_t round /* 
         const unsigned badmask = __ballot_sync(0xffffffffu, bad);
         any |= badmask != 0u;
         n_bad += __popc(badmask);
-        const int dc = parmap_block_scan(m, lane, din);   // the shift chunk c's own start gets this round
+        const int dc = parmap_cta_scan<WPU>(m, lane, w, din, sh_m);   // the shift chunk c's own start gets this round
         bool dirty = false;
         if (valid) {
             float ns = s;
@@ -868,7 +941,11 @@ __global__ void __launch_bounds__(128) k_phase_fix(PlanDev P, uint32_t round /* 
         }
         n_dirty += __popc(dmask);
     }
-    if (lane == 0) {
+    if (CTA) {
+        any = __syncthreads_or(any ? 1 : 0) != 0;
+        if (lane == 0 && w != 0 && n_bad) atomicAdd(P.pstats + PSTAT_MISMATCH, n_bad);   // (warp 0 adds its own below)
+    }
+    if (lane == 0 && w == 0) {
         if (!any) {
             P.utt_status[u] = 1u;                  // proven: k_phase_pair leaves this utterance alone
         } else {

@@ -678,10 +678,12 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
     //      warps of walks per SM (the walks are streaming kernels), at least 1024 samples (a chunk without a carrier
     //      wrap has no anchor: shorter chunks fail their proofs more often), at most 4096.
     pl->phase_chunk = 0;
-    // (A handful of very long utterances -- config 3 -- keep the fixed-point phase scan of grail_kernels.cuh: the
-    //  chunk-parallel path scans an utterance's chunk records with ONE warp per utterance in k_phase_guess / _scan_a /
-    //  _fix, which is the wrong shape for 25 000 chunks of a single utterance: measured 5.8 ms against 3.3 ms.)
-    const bool few_long = ctx->phase_mode == 1 && n_utts <= 16 && n_max >= ctx->pscan_min;
+    // (A handful of very long utterances -- config 3 -- took the fixed-point phase scan of grail_kernels.cuh while the
+    //  per-utterance scans of this path (k_phase_guess / _scan_a / _fix) ran as ONE warp per utterance, the wrong shape
+    //  for 25 000 chunks of a single utterance: 5.8 ms against 3.3 ms.  With a CTA of 32 warps per utterance for such
+    //  plans the chunk-parallel path takes 0.92 ms for the same 26 457 161 samples, bit-identical output; the
+    //  fixed-point scan stays selectable: phase_mode 3.)
+    const bool few_long = ctx->phase_mode == 3 && n_utts <= 16 && n_max >= ctx->pscan_min;
     if (ctx->phase_mode && !few_long && pl->n_items) {
         uint64_t pc = ctx->phase_chunk;
         if (pc == 0) {
@@ -717,6 +719,9 @@ static int plan_build(grail_ctx* ctx, const ElemInput& in, const uint32_t* utt_o
             }
             pc = pc_of(best_k);
         }
+        // long forms: the repairs dominate (five or six rounds, each re-walking most of what lies downstream of a failed
+        // boundary), and they cost per chunk -- measured 1.20 ms at 1 024 against 0.92 ms at 2 048 for config 3
+        if (ctx->phase_chunk == 0 && (uint64_t)n_max / std::max<uint64_t>(pc, 1) >= 4096) pc = std::max<uint64_t>(pc, 2048);
         pc = std::max<uint64_t>(256, (pc + 255) & ~255ull);
         pc = std::min<uint64_t>(pc, pl->chunk_len);
         pl->phase_chunk = (uint32_t)pc;
@@ -1052,11 +1057,16 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
         // repair rounds walk a dense list of dirty chunks whose length only the device knows: fixed grids stride over it
         const unsigned dgc = std::min<unsigned>((pl->n_pchunks + 31) / 32, (unsigned)ctx->prop.multiProcessorCount * 6u);
         const dim3 dgs(std::max(1u, std::min(128u, (pl->n_pchunks + 4095u) / 4096u)), (pl->phase_chunk + 7u) / 8u);
-        k_phase_guess<<<wg, 128, 0, s>>>(P);
+        // the per-utterance scans: a warp per utterance, or -- long forms -- a CTA of 32 warps per utterance
+        const bool cta_scans = pl->max_pchunks >= 2048;
+        auto guess = [&]() { if (cta_scans) k_phase_guess<32><<<pl->n_utts, 1024, 0, s>>>(P); else k_phase_guess<1><<<wg, 128, 0, s>>>(P); };
+        auto scan_a = [&]() { if (cta_scans) k_phase_scan_a<32><<<pl->n_utts, 1024, 0, s>>>(P); else k_phase_scan_a<1><<<wg, 128, 0, s>>>(P); };
+        auto fix = [&](uint32_t r) { if (cta_scans) k_phase_fix<32><<<pl->n_utts, 1024, 0, s>>>(P, r); else k_phase_fix<1><<<wg, 128, 0, s>>>(P, r); };
+        guess();
         pl->last_launches++;
         if (pl->max_pchunks > 1) {
             k_phase_a<<<cg, 128, 0, s>>>(P);
-            k_phase_scan_a<<<wg, 128, 0, s>>>(P);
+            scan_a();
             pl->last_launches += 2;
         }
         k_phase_b<<<cg, 128, 0, s>>>(P, 0u);
@@ -1068,12 +1078,12 @@ static int plan_enqueue(grail_plan* pl, void* d_out, int format, bool with_dbg, 
         if (ctx->phase_rounds >= 0) rounds = std::min(ctx->phase_rounds, (int)PH_MAX_ROUNDS);
         if (pl->max_pchunks <= 1) rounds = 0;
         for (int r = 1; r <= rounds; ++r) {
-            k_phase_fix<<<wg, 128, 0, s>>>(P, (uint32_t)r);
+            fix((uint32_t)r);
             k_phase_chain<<<dgc, 32, 0, s>>>(P, (uint32_t)r);
             k_phase_saw<<<dgs, 512, 0, s>>>(P, (uint32_t)r);   // (y: the blocks of a chunk)
             pl->last_launches += 3;
         }
-        k_phase_fix<<<wg, 128, 0, s>>>(P, (uint32_t)PH_MAX_ROUNDS + 1u);   // the final proof: sets the status bits
+        fix((uint32_t)PH_MAX_ROUNDS + 1u);   // the final proof: sets the status bits
         pl->last_launches++;
     }
     if (pl->n_items) {
@@ -1243,7 +1253,7 @@ int grail_cuda_set_option(grail_ctx* ctx, const char* key, double value)
     } else if (!strcmp(key, "e2e_groups")) {
         ctx->e2e_groups = value < 0.0 ? -1 : (int)value;
     } else if (!strcmp(key, "phase_mode")) {
-        ctx->phase_mode = value == 0.0 ? 0 : (value == 2.0 ? 2 : 1);   // 2: chunk-parallel even for a few long utterances
+        ctx->phase_mode = value == 0.0 ? 0 : (value == 3.0 ? 3 : (value == 2.0 ? 2 : 1));   // 3: fixed-point scan for a few long utterances
     } else if (!strcmp(key, "phase_chunk")) {
         if (value != 0.0 && !(value >= 256.0 && value <= 1048576.0)) return set_err(ctx, GRAIL_ERR_INVALID_ARG, "phase_chunk out of range [256, 2^20] (0 = auto)");
         ctx->phase_chunk = (uint32_t)value;

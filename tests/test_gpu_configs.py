@@ -19,29 +19,52 @@ def ctx():
     c.close()
 
 
-def test_config3_long_form(ctx, oracle):
-    """one 10-minute utterance: 26 457 161 samples, one chain, 1 200 phonemes"""
-    elems, offs, vp = W.config3(1200)
-    plan = ctx.plan(elems, offs, vp)
-    assert plan.total_samples == 26457161
-    plan.launch()
-    out = plan.read_output()
-    ps = plan.phase_scan_stats()
-    print(plan.timings(), ps)
-    assert ps["scans"] == 1 and ps["converged"] == 1 and ps["refused"] == 0      # parallel-in-time phase scan, no serial chain
-    f, ph, saw = plan.read_intermediates()
-    want, tr, fin = oracle.synthesize(elems, vp[0], trace=True)
-    assert np.array_equal(f.view(np.uint32), tr["frequency"].view(np.uint32))          # bit-exact fundamental
-    assert np.array_equal(ph.view(np.uint32), tr["carrier_phase"].view(np.uint32))     # bit-exact carrier phase
-    st = W.parity_stats(out, want)
-    print(st)
-    assert st["max_abs"] <= MAX_ABS and st["snr_db"] >= MIN_SNR_DB, st
-    plan.close()
+_CONFIG3 = {}
+
+
+def _config3_oracle(oracle):
+    if not _CONFIG3:
+        elems, offs, vp = W.config3(1200)
+        want, tr, fin = oracle.synthesize(elems, vp[0], trace=True)
+        _CONFIG3.update(elems=elems, offs=offs, vp=vp, want=want, tr=tr)
+    return _CONFIG3
+
+
+@pytest.mark.parametrize("phase_mode", [1, 3])
+def test_config3_long_form(ctx, oracle, phase_mode):
+    """one 10-minute utterance: 26 457 161 samples, one chain, 1 200 phonemes.  phase_mode 1 (the
+    default): the chunk-parallel exact phase with CTA-wide scans over the utterance's ~13 000 chunks; phase_mode 3: the
+    fixed-point phase scan.  Two unrelated exact algorithms, the same bits."""
+    c3 = _config3_oracle(oracle)
+    elems, offs, vp, want, tr = c3["elems"], c3["offs"], c3["vp"], c3["want"], c3["tr"]
+    ctx.set_option("phase_mode", phase_mode)
+    try:
+        plan = ctx.plan(elems, offs, vp)
+        assert plan.total_samples == 26457161
+        plan.launch()
+        out = plan.read_output()
+        if phase_mode == 3:
+            ps = plan.phase_scan_stats()
+            print(plan.timings(), ps)
+            assert ps["scans"] == 1 and ps["converged"] == 1 and ps["refused"] == 0      # parallel-in-time phase scan, no serial chain
+        else:
+            ps = plan.phase_stats()
+            print(plan.timings(), ps)
+            assert ps["chunks"] >= 2048 and ps["unproven_utterances"] == 0, ps             # proven chunk by chunk, no serial chain
+        f, ph, saw = plan.read_intermediates()
+        assert np.array_equal(f.view(np.uint32), tr["frequency"].view(np.uint32))          # bit-exact fundamental
+        assert np.array_equal(ph.view(np.uint32), tr["carrier_phase"].view(np.uint32))     # bit-exact carrier phase
+        st = W.parity_stats(out, want)
+        print(st)
+        assert st["max_abs"] <= MAX_ABS and st["snr_db"] >= MIN_SNR_DB, st
+        plan.close()
+    finally:
+        ctx.set_option("phase_mode", 1)
 
 
 def test_long_form_chunk_parallel_phase(ctx, oracle):
-    """the chunk-parallel walk forced onto one long utterance (phase_mode 2; 120 phonemes, 2.6 M samples, ~1 300 chunks
-    scanned by a single warp): carrier phase bit-exact, every utterance proven"""
+    """the chunk-parallel walk on one long utterance below the CTA-scan threshold (120 phonemes, 2.6 M samples, ~1 300
+    chunks scanned by a single warp): carrier phase bit-exact, every utterance proven"""
     elems, offs, vp = W.from_phonemes([W.config3_phonemes(120)], g.voices.generic(), [0])
     ctx.set_option("phase_mode", 2)
     try:
