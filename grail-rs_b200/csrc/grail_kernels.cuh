@@ -287,14 +287,28 @@ __device__ __forceinline__ FreqSeg load_freq_seg(const float* ue, uint32_t p, ui
 // (one voice, interleaved chunks), but 0.478 / 0.648 / 0.605 ms on a config-4 slice (a voice per utterance, whole
 // utterances as items): the planner takes 512 when the batch shares one jitter schedule and 256 otherwise.
 constexpr int FREQ_RUN_MAX = 512;
+#ifndef KFREQ_LANE_IS_ITEM
+#define KFREQ_LANE_IS_ITEM 1
+#endif
 
 __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_item, uint32_t run_len)
 {
-    // lanes of a warp = consecutive runs of one item (measured against "the same run of 32 consecutive items", which
-    // lines events up across lanes but scatters every per-utterance load: 0.36 vs 0.39 ms at config 2)
+    // Lane mapping.  Until F_t moved into the saw's tiled layout the lanes of a warp were consecutive runs of ONE item; ncu
+    // then showed the kernel waiting on its own stores (the loop's back edge parked on the store scoreboard, 17 % of all
+    // samples; lg_throttle): 32 lanes x 16 bytes into 32 different 1 KB tiles per instruction.  Measured at config 2:
+    // 0.293 ms -> 0.247 ms with one 256-bit store per lane -> 0.212 ms with lane = item (config-4 slice 0.48 -> 0.37 ms).
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+#if KFREQ_LANE_IS_ITEM
+    // a warp = the same run of the 32 items of one k_formant group: with F_t in the tiled layout its 32 lanes store
+    // 1 KB of consecutive addresses per 8-sample block (one 256-bit store per lane), and with a shared voice the
+    // value-noise wraps and hand-overs fall on the same samples in every lane
+    const uint64_t wid = t >> 5;
+    const uint32_t item = (uint32_t)(wid / runs_per_item) * 32u + (uint32_t)(t & 31u);
+    const uint32_t run = (uint32_t)(wid % runs_per_item);
+#else
     const uint32_t item = (uint32_t)(t / runs_per_item);
     const uint32_t run = (uint32_t)(t % runs_per_item);
+#endif
     if (item >= P.n_items) return;
     const ItemDev it = P.items[item];
     const uint32_t off = run * run_len;
@@ -384,9 +398,10 @@ __global__ void __launch_bounds__(128) k_frequency(PlanDev P, uint32_t runs_per_
                     jph = sadd(jph, jinc);                                                     // :242
                 }
             }
-            float4* d4 = reinterpret_cast<float4*>(dst + (k0 >> 3) * bstep);
-            d4[0] = make_float4(buf[0], buf[1], buf[2], buf[3]);
-            d4[1] = make_float4(buf[4], buf[5], buf[6], buf[7]);
+            float* d8 = dst + (k0 >> 3) * bstep;
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(d8), "f"(buf[0]), "f"(buf[1]), "f"(buf[2]), "f"(buf[3]),
+                         "f"(buf[4]), "f"(buf[5]), "f"(buf[6]), "f"(buf[7])
+                         : "memory");
         } else {
             const uint32_t kend = min(k0 + 8, count);
 #pragma unroll 1

@@ -1,2 +1,7 @@
-python -m pytest tests -m gpu -q 2>&1 | tail -4
-python bench.py --config 3 --steps 10 > gpurun_out/f2_c3_n1.json 2> gpurun_out/f2_c3_n1.err; head -c 330 gpurun_out/f2_c3_n1.json; echo; python scripts/cfg3_time.py 2>&1 | head -2
+python scripts/prof_cfg2.py 4 2>&1 | tail -1 | sed "s/^/new cfg2: /" | cut -c1-220
+GRAIL_CUDA_LIB=/root/repo/_variants/libgrail_lk0.so python scripts/prof_cfg2.py 4 2>&1 | tail -1 | sed "s/^/old cfg2: /" | cut -c1-220
+GRAIL_CFG=4 python scripts/prof_cfg2.py 4 2>&1 | tail -1 | sed "s/^/new cfg4: /" | cut -c1-220
+GRAIL_CFG=4 GRAIL_CUDA_LIB=/root/repo/_variants/libgrail_lk0.so python scripts/prof_cfg2.py 4 2>&1 | tail -1 | sed "s/^/old cfg4: /" | cut -c1-220
+GRAIL_CFG=3 python scripts/prof_cfg2.py 4 2>&1 | tail -1 | sed "s/^/new cfg3: /" | cut -c1-220
+GRAIL_CFG=3 GRAIL_CUDA_LIB=/root/repo/_variants/libgrail_lk0.so python scripts/prof_cfg2.py 4 2>&1 | tail -1 | sed "s/^/old cfg3: /" | cut -c1-220
+python -m pytest tests -m gpu -q -x 2>&1 | tail -3
