@@ -35,3 +35,9 @@ ctx.set_option("pscan_min_samples", 1 << 18); ctx.set_option("pscan_cost_model",
 ctx.set_option("min_chunk", 2048); ctx.set_option("target_lanes", 1 << 20)
 plan = ctx.plan_phonemes(ids, poffs, v.storage(), pvp, center_frequency=np.full(len(lists), v.center_frequency, np.float32))
 plan.launch(); o = plan.read_output(); print("phonemes", len(o), float(np.abs(o).sum())); plan.close()
+# a long utterance whose chunk records are scanned by a CTA of 32 warps (>= 2048 phase chunks of 256 samples)
+ctx.set_option("min_chunk", 2048); ctx.set_option("target_lanes", 0); ctx.set_option("phase_chunk", 256)
+el, ol, vl = W.from_phonemes([W.config3_phonemes(28)], g.voices.generic(), [5])
+plan = ctx.plan(el, ol, vl)
+plan.launch(); o = plan.read_output(); print("long form", len(o), plan.phase_stats()); plan.close()
+ctx.set_option("phase_chunk", 0)
