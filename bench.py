@@ -434,6 +434,15 @@ def run_ours(args):
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     total_samples = D.sum(float(n_samples))          # all ranks (config 2: N x the batch; config 4: the one batch)
     value = total_samples * args.steps / (ms * 1e-3)
+    # the same K steps launched in order (no overlap between consecutive steps), for the record: `value` above uses the
+    # plan option "pipeline" unless --pipeline 0
+    in_order = None
+    if args.pipeline and args.config in (2, 3):
+        plan_io = ctx.plan(elems, offs, vp)          # (the ctx option is back to 0 here)
+        ms_io, _, _ = timed_resident(D, ctx, plan_io, d_out, args.steps, args.warmup)
+        in_order = {"value": total_samples * args.steps / (ms_io * 1e-3), "unit": UNIT, "ms_per_step": ms_io / args.steps,
+                    "note": "the same plan without the pipeline option: every step's kernels in stream order"}
+        plan_io.close()
     reps = max(3, min(args.steps, 10))
     kern = kernel_split(ctx, plan, d_out, reps)
     launches = plan.timings()["n_launches"] * args.steps
@@ -551,6 +560,8 @@ def run_ours(args):
         }
         if e2e_i16 is not None:
             line["e2e_i16"] = e2e_i16
+        if in_order is not None:
+            line["in_order"] = in_order
         if cfg4 is not None:
             line["config4"] = cfg4
     plan.close()
