@@ -1778,39 +1778,82 @@ static int streams_pull_impl(grail_stream* const* streams, uint32_t n_streams, f
     std::vector<uint32_t> offs(nl + 1, 0);
     std::vector<grail_voice_params> voices(nl);
     std::vector<StreamStart> ss(nl);
-    for (uint32_t i = 0; i < nl; ++i) {
-        grail_stream* s = streams[live[i]];
-        elems.insert(elems.end(), s->pending.begin(), s->pending.end());
-        offs[i + 1] = (uint32_t)elems.size();
-        voices[i] = s->voice;
-        ss[i] = s->st;
-        ss[i].filter_state = s->st.fresh ? nullptr : s->filter;
-        ss[i].max_samples = std::min<uint64_t>(max_samples[live[i]], MAX_UTT_SAMPLES);
-        ss[i].finished = s->finished;
-    }
+    // Only the phonemes a window can reach go into the plan (a stream that was pushed a whole sentence holds dozens of
+    // 208-byte records; a 10 ms window needs one or two): the phoneme in progress counts for nothing, every further one
+    // for a little less than length * sample_rate, until the window is covered -- plus one more as the look-ahead.  A
+    // shortened list is planned as "unfinished" (its last record is held back like any look-ahead).  Should a window
+    // still come out short (lengths that are not numbers), the call is planned again with everything.
+    auto reach = [&](const grail_stream* s, uint64_t want) -> size_t {
+        const size_t np = s->pending.size();
+        const double rate = (double)s->voice.sample_rate;
+        double acc = 0.0;
+        size_t k = 1;
+        for (; k < np && acc < (double)want; ++k) {
+            const double n = (double)s->pending[k].length * rate * 0.999 - 4.0;
+            if (n > 0.0) acc += n;             // (NaN compares false: counts for nothing)
+        }
+        return std::min(np, k + 1);
+    };
     grail_plan* pl = nullptr;
-    ElemInput in;
-    in.full = elems.data();
-    int rc = plan_build(ctx, in, offs.data(), voices.data(), nl, &pl, ss.data());
-    if (rc) return rc;
+    int rc = GRAIL_OK;
+    std::vector<uint8_t> cut(nl, 0);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        elems.clear();
+        for (uint32_t i = 0; i < nl; ++i) {
+            grail_stream* s = streams[live[i]];
+            const uint64_t want = std::min<uint64_t>(max_samples[live[i]], MAX_UTT_SAMPLES);
+            const size_t take = attempt == 0 ? reach(s, want) : s->pending.size();
+            cut[i] = take < s->pending.size();
+            elems.insert(elems.end(), s->pending.begin(), s->pending.begin() + take);
+            offs[i + 1] = (uint32_t)elems.size();
+            voices[i] = s->voice;
+            ss[i] = s->st;
+            ss[i].filter_state = s->st.fresh ? nullptr : s->filter;
+            ss[i].max_samples = want;
+            ss[i].finished = s->finished && !cut[i];
+        }
+        ElemInput in;
+        in.full = elems.data();
+        rc = plan_build(ctx, in, offs.data(), voices.data(), nl, &pl, ss.data());
+        if (rc) return rc;
+        bool short_window = false;
+        for (uint32_t i = 0; i < nl && !short_window; ++i)
+            short_window = cut[i] && pl->utts[i].n_samples < ss[i].max_samples;
+        if (!short_window) break;
+        cudaStreamSynchronize(ctx->stream);
+        plan_release(pl);
+        pl = nullptr;
+    }
+    if (!pl) return set_err(ctx, GRAIL_ERR_CUDA, "stream window could not be planned");
     std::vector<float> fin((size_t)nl * 32, 0.0f);
     if (pl->total_samples) {
         void* d = nullptr;
         rc = grail_cuda_plan_device_output(pl, GRAIL_F32, &d);
         if (!rc) rc = plan_enqueue(pl, d, GRAIL_F32, false, true);
+        // Read-back: ONE copy of the filter states and ONE of the packed windows into a pinned block, then host copies
+        // into the callers' buffers.  (A cudaMemcpyAsync per stream into pageable memory is a synchronous staged copy
+        // each: 16-20 us per stream and tick, which capped a tick of 1 024 streams at 20 ms.)
+        const size_t fin_bytes = fin.size() * sizeof(float), out_bytes = (size_t)pl->total_samples * sizeof(float);
+        void* hst = nullptr;
+        if (!rc) rc = hpool_alloc(ctx, fin_bytes + out_bytes + 256, &hst);
         cudaError_t e = cudaSuccess;
-        if (!rc) e = cudaMemcpyAsync(fin.data(), pl->d_utt_final, fin.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
-        for (uint32_t i = 0; i < nl && !rc && e == cudaSuccess; ++i) {
-            const uint64_t n = pl->utts[i].n_samples;
-            if (n) e = cudaMemcpyAsync(outs[live[i]], (const float*)d + pl->out_offsets[i], n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
-        }
+        if (!rc) e = cudaMemcpyAsync(hst, pl->d_utt_final, fin_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        if (!rc && e == cudaSuccess) e = cudaMemcpyAsync((char*)hst + fin_bytes, d, out_bytes, cudaMemcpyDeviceToHost, ctx->stream);
         if (!rc && e != cudaSuccess) rc = set_err(ctx, GRAIL_ERR_CUDA, "stream read-back failed: %s", cudaGetErrorString(e));
         if (!rc) rc = plan_check_device_errors(pl);             // synchronizes the stream
         if (rc) {
             cudaStreamSynchronize(ctx->stream);
+            hpool_free(ctx, hst);
             plan_release(pl);
             return rc;
         }
+        memcpy(fin.data(), hst, fin_bytes);
+        const float* hout = reinterpret_cast<const float*>((const char*)hst + fin_bytes);
+        for (uint32_t i = 0; i < nl; ++i) {
+            const uint64_t n = pl->utts[i].n_samples;
+            if (n) memcpy(outs[live[i]], hout + pl->out_offsets[i], n * sizeof(float));
+        }
+        hpool_free(ctx, hst);
     }
     // ---- every stream's iterator state after its last sample, from the exact host-side schedules
     for (uint32_t i = 0; i < nl; ++i) {

@@ -124,3 +124,34 @@ def test_batched_streams_pull_equals_separate_streams(ctx, oracle):
         stats = W.parity_stats(y, wants[k])
         assert stats["max_abs"] <= 1e-4 and stats["snr_db"] >= 90.0, (k, stats)
         st.close()
+
+
+def test_stream_windows_spanning_many_short_phonemes(ctx, oracle):
+    """a sentence of very short phonemes (3-40 ms, some of zero length) pushed at once: a window needs only the next few of
+    the pending records, and the library plans just those -- every window must still be full (until the stream ends) and
+    the concatenation must equal the one-shot rendering"""
+    rng = np.random.default_rng(5)
+    phon = [int(p) for p in rng.integers(3, 5, 120)]
+    elems, offs, vp = W.from_phonemes([phon], g.voices.generic(), [21])
+    elems = elems.copy()
+    ln = rng.uniform(0.003, 0.04, 120).astype(np.float32)
+    ln[[7, 8, 50]] = 0.0
+    elems["length"] = ln
+    elems["blend_length"] = np.maximum(ln, np.float32(0.002))
+    want, _, _ = oracle.synthesize(elems, vp[0])
+    for window in (441, 5000):
+        st = ctx.stream(vp[0])
+        st.push(elems)
+        st.finish()
+        got = []
+        while True:
+            x = st.pull(window)
+            if len(x) == 0:
+                break
+            got.append(x.copy())
+        st.close()
+        assert all(len(x) == window for x in got[:-1])       # only the last window may be short
+        got = np.concatenate(got)
+        assert len(got) == len(want)
+        stats = W.parity_stats(got, want)
+        assert stats["max_abs"] <= 1e-4 and stats["snr_db"] >= 90.0, stats
