@@ -1,5 +1,3 @@
-for v in default kt64 kt128; do
-  if [ $v = default ]; then L=""; else L="GRAIL_CUDA_LIB=/root/repo/_variants/libgrail_$v.so"; fi
-  env $L python scripts/prof_cfg2.py 4 2>&1 | tail -1 | sed "s/^/$v cfg2: /" | cut -c1-200
-  env $L GRAIL_CFG=4 python scripts/prof_cfg2.py 4 2>&1 | tail -1 | sed "s/^/$v cfg4: /" | cut -c1-200
-done
+python -m pytest tests -m gpu -q 2>&1 | tail -3
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_bench_steps2.csv python bench.py --steps 2 --warmup 3 > gpurun_out/r2_bench_under_ncu.log 2>&1
+grep -c k_formant gpurun_out/r2_launches_bench_steps2.csv
