@@ -339,3 +339,19 @@ def test_division_by_segment_constant_is_ieee_exact(ctx):
     bad = C.c_uint64(123)
     rc = ctx._L.grail_cuda_debug_div_check(ctx._h, 20261017, 1 << 31, C.byref(bad))
     assert rc == 0 and bad.value == 0, (rc, bad.value)
+
+
+def test_jitter_frequency_extremes(ctx, oracle):
+    """value-noise increments from 0 to the largest the path accepts (0.25: a wrap every 4 samples), around the 1/17 and
+    1/9 thresholds where k_formant's blocks stop being split / interpolated: counts, F_t and phase bit-exact, audio in
+    tolerance -- in ONE batch, so that the 32 lanes of a warp disagree about which path a block takes"""
+    incs = [0.0, 1e-6, 1.0 / 2756.0, 0.01, 1.0 / 17.0, 0.0588235, 0.06, 0.1, 1.0 / 9.0, 0.12, 0.2, 0.25]
+    lists = [[0, 3, 4][: 1 + (k % 3)] + [4, 3] for k in range(len(incs))]
+    elems, offs, vp = W.from_phonemes(lists, g.voices.generic(), list(range(40, 40 + len(incs))))
+    elems = elems.copy()
+    elems["length"] = np.float32(0.05)
+    elems["blend_length"] = np.float32(0.03)
+    vp = vp.copy()
+    vp["jitter_frequency"] = np.asarray(incs, np.float32)
+    worst, out, oo = check_batch(ctx, oracle, elems, offs, vp, label="jitter extremes")
+    print(worst)
