@@ -118,6 +118,9 @@ int  grail_cuda_synchronize(grail_ctx* ctx);
  * "pscan_cost_model" (0|1), "zero_copy_out" (0|1), "interleave" (0|1: interleave equally long utterances chunk by
  * chunk in the formant kernel's CTAs), "phase_lean" (-1 auto | 0 | 1: which build of the phase kernel) */
 int  grail_cuda_set_option(grail_ctx* ctx, const char* key, double value);
+/* Environment (diagnostics only): GRAIL_E2E_TRACE=1 prints the timeline of every one-shot batch call on stderr (per
+ * utterance group: host time at enqueue, device times of kernels-done and copy-done); GRAIL_PLAN_TRACE=1 prints the host
+ * planner's phases per plan. */
 
 /* pinned host memory for full-rate H2D/D2H (optional; pageable buffers also work) */
 int  grail_cuda_host_alloc(grail_ctx* ctx, size_t bytes, void** out_ptr);
