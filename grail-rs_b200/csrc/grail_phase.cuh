@@ -606,10 +606,18 @@ __device__ __forceinline__ uint32_t wrap_tie1(float p, float f)
     return 0u;
 }
 // Blocks that hold a polyBLEP edge sample (the sample before and the sample after a carrier wrap: 2 in ~370 at
-// 120 Hz) are only NOTED by the walk -- tiled offset and the phase at the block's start -- and redone afterwards, one
-// block at a time: the divisions of the polyBLEP and the tie test then cost a lane what its own wraps cost, instead of
-// every lane of the warp paying for every other lane's wraps inside the hot loop.
+// 120 Hz).  First version (PH_INLINE_EDGES 0): such a block is only NOTED by the walk -- tiled offset and the phase at the
+// block's start -- and redone afterwards, one block at a time, so that the divisions of the polyBLEP and the tie test
+// cost a lane what its own wraps cost, instead of every lane of the warp paying for every other lane's wraps inside the
+// hot loop.  Measured wrong: the kernel has issue slots to spare (38 % busy) but saturates the memory system, and every
+// redo waited a full DRAM round trip for the block's eight increments under that load -- about 5 us each, three per
+// chunk, a tenth of the kernel (ncu: 7 % of all stall samples on one instruction of the redo).  Keeping the increments
+// in the note (local memory) was worse still.  Now the edge samples are fixed in place, while the block's increments
+// and phases are in registers: 355 -> 326 us at config 2 (config-4 slice, phase total: 0.96 -> 0.87 ms), same bits.
 constexpr int PH_EDGE_BUF = 24;
+#ifndef PH_INLINE_EDGES
+#define PH_INLINE_EDGES 1
+#endif
 
 __device__ __noinline__ uint32_t phase_b_redo_block(const float* __restrict__ F, float* __restrict__ saw, size_t off, float p,
                                                     uint32_t want_tie)
@@ -655,6 +663,9 @@ __global__ void __launch_bounds__(128, PH_OCC) k_phase_b(PlanDev P, uint32_t rou
     float* dbg = P.phase_dbg ? P.phase_dbg + U.f_off : nullptr;
     float p = pcf(P, PCF_START)[g];
     uint32_t tie = 0u;
+#if PH_INLINE_EDGES
+    auto flush = []() {};
+#else
     // note pad: the tiled offsets fit 32 bits in units of 8 floats (2^35 floats)
     uint32_t eb_off[PH_EDGE_BUF];
     float eb_p[PH_EDGE_BUF];
@@ -667,27 +678,41 @@ __global__ void __launch_bounds__(128, PH_OCC) k_phase_b(PlanDev P, uint32_t rou
         }
         eb_n = 0;
     };
+#endif
     const uint32_t n1f = n1 & ~7u;                  // whole blocks; only an utterance's last chunk has a ragged tail
     walk_blocks(ring, F, U, CL, n0, n1f, [&](uint32_t blk, size_t off, const float (&f)[8]) -> bool {
         float pv[8], s[8];
         bool edge = false;
+        uint32_t wraps = 0u;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {                       // :520-525
             pv[k] = p;
             float gk;
             p = phase_step(p, f[k], gk);
+            wraps |= (gk != 0.0f ? 1u : 0u) << k;
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             s[k] = fmaf(2.0f, pv[k], -1.0f);                                    // :517 with polyblep = 0 (2p is exact)
             edge |= !((pv[k] >= f[k]) && (pv[k] <= ssub(1.0f, f[k]))) || !(p >= pv[k]);   // (second test: any wrap inside the block, or a NaN: its tie test)
         }
+#if PH_INLINE_EDGES
+        if (edge) {                                          // the polyBLEP samples and the tie test, in place
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (!((pv[k] >= f[k]) && (pv[k] <= ssub(1.0f, f[k])))) s[k] = saw_edge(pv[k], f[k]);
+                if (tie == 0u && ((wraps >> k) & 1u)) tie = wrap_tie1(pv[k], f[k]);
+            }
+        }
+        stg256(P.saw + off, s);
+#else
         stg256(P.saw + off, s);
         if (edge) {                                          // noted; redone after the walk (or when the note pad is full)
             eb_off[eb_n] = (uint32_t)(off >> 3);
             eb_p[eb_n] = pv[0];
             if (++eb_n == PH_EDGE_BUF) flush();
         }
+#endif
         if (dbg) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) dbg[blk + k] = pv[k];

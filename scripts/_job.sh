@@ -1,4 +1,4 @@
-for v in default swap; do
-  if [ $v = default ]; then L=""; else L="GRAIL_CUDA_LIB=/root/repo/_variants/libgrail_$v.so"; fi
-  env $L python scripts/pipeline_test.py 2>&1 | head -2 | cut -c1-110 | sed "s/^/$v: /"
-done
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_phase_b -c 1 python scripts/prof_cfg2.py 1 2>&1 | grep -E "gpu__time_duration" | sed "s/^/new B: /"
+python scripts/prof_cfg2.py 4 2>&1 | tail -1 | cut -c1-200
+GRAIL_CFG=4 python scripts/prof_cfg2.py 4 2>&1 | tail -1 | cut -c1-200
+python -m pytest tests -m gpu -q -x 2>&1 | tail -2
