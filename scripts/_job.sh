@@ -1,4 +1,7 @@
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_phase_b -c 1 python scripts/prof_cfg2.py 1 2>&1 | grep -E "gpu__time_duration" | sed "s/^/new B: /"
-python scripts/prof_cfg2.py 4 2>&1 | tail -1 | cut -c1-200
-GRAIL_CFG=4 python scripts/prof_cfg2.py 4 2>&1 | tail -1 | cut -c1-200
-python -m pytest tests -m gpu -q -x 2>&1 | tail -2
+O=gpurun_out
+python bench.py > $O/f5_c2_n1.json 2> $O/f5_c2_n1.err
+python bench.py --config 3 --steps 10 > $O/f5_c3_n1.json 2> $O/f5_c3_n1.err
+python bench.py --config 4 --steps 5 > $O/f5_c4_n1.json 2> $O/f5_c4_n1.err
+python bench.py --config 5 --steps 5 > $O/f5_c5_n1.json 2> $O/f5_c5_n1.err
+bash scripts/make_profiles.sh > $O/r2_make_profiles.log 2>&1
+for f in $O/f5_*.json; do echo == $f; head -c 230 $f; echo; done
