@@ -683,13 +683,11 @@ __global__ void __launch_bounds__(128, PH_OCC) k_phase_b(PlanDev P, uint32_t rou
     walk_blocks(ring, F, U, CL, n0, n1f, [&](uint32_t blk, size_t off, const float (&f)[8]) -> bool {
         float pv[8], s[8];
         bool edge = false;
-        uint32_t wraps = 0u;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {                       // :520-525
             pv[k] = p;
             float gk;
             p = phase_step(p, f[k], gk);
-            wraps |= (gk != 0.0f ? 1u : 0u) << k;
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -701,7 +699,7 @@ __global__ void __launch_bounds__(128, PH_OCC) k_phase_b(PlanDev P, uint32_t rou
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 if (!((pv[k] >= f[k]) && (pv[k] <= ssub(1.0f, f[k])))) s[k] = saw_edge(pv[k], f[k]);
-                if (tie == 0u && ((wraps >> k) & 1u)) tie = wrap_tie1(pv[k], f[k]);
+                if (tie == 0u) tie = wrap_tie1(pv[k], f[k]);           // (tests for the wrap itself)
             }
         }
         stg256(P.saw + off, s);
